@@ -1,0 +1,165 @@
+/*
+ * pmw.h -- C ABI of the B200-native PyMiniWeather hot path (libpmw.so).
+ *
+ * The reference (shriram-jagan/pyminiweather) is pure Python and has no FFI of
+ * its own; its only backend seam is the array-module alias in
+ * pyminiweather/__init__.py:4-9.  The boundary this library plugs into is
+ * therefore the set of Python operator functions the reference's driver calls
+ * (pyminiweather/__main__.py:205,214,237,239).  Each entry point below names
+ * the reference function (file:line, relative to the reference repo) whose work
+ * it performs.  INTEGRATION.md shows the ctypes stub a reference maintainer
+ * would add to bind them.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (PMW_OK) on success or a
+ *     negative PMW_E* code, and pmw_last_error() then returns a thread-local
+ *     human-readable message;
+ *   - host state arrays use the reference layout: double [4][nz+4][nx+4], C
+ *     order, variables DENS=0, UMOM=1, WMOM=2, RHOT=3
+ *     (pyminiweather/__init__.py:14-18, pyminiweather/data/fields.py:67-72);
+ *   - a context owns its device buffers; the caller owns every host pointer;
+ *   - calls on one context are not thread-safe; contexts are independent;
+ *   - all work is enqueued on the context's stream (pmw_set_stream); functions
+ *     that return data to the host synchronise that stream.
+ */
+#ifndef PMW_H_
+#define PMW_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMW_OK 0
+#define PMW_EINVAL (-1)  /* bad argument */
+#define PMW_ECUDA (-2)   /* CUDA runtime/driver error */
+#define PMW_ESTATE (-3)  /* call not valid in the current state */
+
+/* logical state buffers (pyminiweather/data/fields.py:20-21) */
+#define PMW_BUF_STATE 0 /* fields.state      */
+#define PMW_BUF_TMP 1   /* fields.state_tmp  */
+
+/* pyminiweather/ics/directions.py:4-6 */
+#define PMW_DIR_X 1
+#define PMW_DIR_Z 2
+
+/* kernel variants (pmw_params.variant) */
+#define PMW_VARIANT_DIRECT 0 /* one thread per cell, operands through L1/L2        */
+#define PMW_VARIANT_TMA 1    /* TMA-staged shared-memory tiles (the production path) */
+
+/* pressure evaluation (pmw_params.pow_mode) */
+#define PMW_POW_LIBDEVICE 0 /* p = C0 * pow(rho*theta, gamma), CUDA math library      */
+#define PMW_POW_BACKGROUND 1 /* p = P_hy(z) * (1+eps)^gamma via a degree-12 polynomial in
+                                eps = (rho*theta - (rho*theta)_hy)/(rho*theta)_hy, falling
+                                back to pow() when |eps| > 1/8                         */
+
+typedef struct pmw_ctx pmw_ctx;
+
+typedef struct pmw_params {
+    int nx;       /* interior columns held by THIS context (slab width), >= 4       */
+    int nz;       /* interior rows, >= 4                                            */
+    int hs;       /* halo width; must be 2 (pyminiweather/__main__.py:92-100)       */
+    double dx;    /* params["dx"]                                                   */
+    double dz;    /* params["dz"]                                                   */
+    double dt;    /* params["dt"], the FULL step: the hyperviscosity coefficient uses
+                     it in every stage (pyminiweather/solve/interpolate.py:99-101)  */
+    int device;   /* CUDA device ordinal                                            */
+    int variant;  /* PMW_VARIANT_*                                                  */
+    int pow_mode; /* PMW_POW_*                                                      */
+    int periodic_x; /* 1: this context wraps its own x halos (single slab, the
+                       reference's set_bc_x); 0: x halos arrive from slab neighbours
+                       through pmw_unpack_halo_x / peer stores                      */
+} pmw_params;
+
+const char *pmw_last_error(void);
+int pmw_version(void);
+
+/* -- lifetime ------------------------------------------------------------------ */
+/* Allocates three state buffers + profiles on params->device.
+ * Replaces the allocation half of initialize_fields (pyminiweather/data/fields.py:58-123);
+ * the interpolation/flux/tendency scratch arrays of that function do not exist here. */
+int pmw_create(const pmw_params *params, pmw_ctx **out);
+int pmw_destroy(pmw_ctx *ctx);
+/* cudaStream_t as void*; NULL = the legacy default stream. */
+int pmw_set_stream(pmw_ctx *ctx, void *cuda_stream);
+int pmw_synchronize(pmw_ctx *ctx);
+
+/* -- data movement ------------------------------------------------------------- */
+/* The five 1-D hydrostatic profiles produced by init (pyminiweather/ics/initial.py:84-105):
+ * hy_dens_cell[nz+4], hy_dens_theta_cell[nz+4], hy_dens_int[nz+1],
+ * hy_dens_theta_int[nz+1], hy_pressure_int[nz+1]. */
+int pmw_set_hydrostatic(pmw_ctx *ctx, const double *hy_dens_cell, const double *hy_dens_theta_cell,
+                        const double *hy_dens_int, const double *hy_dens_theta_int,
+                        const double *hy_pressure_int);
+/* host [4][nz+4][nx+4] <-> device buffer `buf` (PMW_BUF_*).  Synchronous. */
+int pmw_upload_state(pmw_ctx *ctx, int buf, const double *host);
+int pmw_download_state(pmw_ctx *ctx, int buf, double *host);
+/* Asynchronous variants on the context stream (host memory should be pinned). */
+int pmw_upload_state_async(pmw_ctx *ctx, int buf, const double *host);
+int pmw_download_state_async(pmw_ctx *ctx, int buf, double *host);
+
+/* -- operators (one call = one reference function) ------------------------------- */
+/* set_bc_x, periodic branch (pyminiweather/ics/bcs.py:35-39). */
+int pmw_bc_x(pmw_ctx *ctx, int buf);
+/* set_bc_z (pyminiweather/ics/bcs.py:92-148). */
+int pmw_bc_z(pmw_ctx *ctx, int buf);
+/* discrete_step WITHOUT its leading set_bc_* call (pyminiweather/solve/step.py:67-82 minus
+ * :68/:73): interpolate + flux + tendency (+ hydrostatic source in z) + stage update,
+ * fused.  out may alias init and/or forcing exactly as in step.py:112-141. */
+int pmw_stage(pmw_ctx *ctx, int direction, int init_buf, int forcing_buf, int out_buf,
+              double dt_stage);
+/* discrete_step as the reference runs it: set_bc_* on forcing, then pmw_stage
+ * (pyminiweather/solve/step.py:21-82). */
+int pmw_discrete_step(pmw_ctx *ctx, int direction, int init_buf, int forcing_buf, int out_buf,
+                      double dt_stage);
+/* nsteps x evolve (pyminiweather/solve/step.py:85-143): two directional sweeps of three RK
+ * stages per step, Z first on the first call, order alternating per step; the direction
+ * flag (a module global in the reference, step.py:18) lives in the context.  Halo fill is
+ * folded into the stage kernels.  dt <= 0 means params.dt. */
+int pmw_evolve(pmw_ctx *ctx, int nsteps, double dt);
+/* One RK stage (rk_stage = 1,2,3) of the fused step on the context's rotating buffers, for
+ * callers that interleave their own work between stages (slab halo exchange).  The caller
+ * sequences directions/stages as evolve does and flips the direction flag itself. */
+int pmw_evolve_stage(pmw_ctx *ctx, int direction, int rk_stage, double dt);
+int pmw_get_reverse_direction(pmw_ctx *ctx, int *reverse);
+int pmw_set_reverse_direction(pmw_ctx *ctx, int reverse);
+/* compute_stats (pyminiweather/post/stats.py:8-35): out[0] = total mass, out[1] = total
+ * energy of buffer `buf`, over this context's interior, already scaled by dx*dz. */
+int pmw_stats(pmw_ctx *ctx, int buf, double out[2]);
+/* Same sums left on the device (2 doubles, already scaled) for an NCCL all-reduce. */
+int pmw_stats_device(pmw_ctx *ctx, int buf, double *dev_out2);
+/* compute_solution_variables (pyminiweather/post/stats.py:38-69): host [4][nz][nx]. */
+int pmw_solution_variables(pmw_ctx *ctx, int buf, double *host_out);
+
+/* -- x-slab sharding (one context per GPU) ---------------------------------------- */
+/* Edge columns of `buf` as two contiguous device messages of pmw_halo_len() doubles each
+ * ([4][nz][2]): to_left = my first two interior columns, to_right = my last two.  This is
+ * set_bc_x (bcs.py:35-39) generalised to a ring of slabs. */
+size_t pmw_halo_len(pmw_ctx *ctx);
+int pmw_pack_halo_x(pmw_ctx *ctx, int buf, double *dev_to_left, double *dev_to_right);
+int pmw_unpack_halo_x(pmw_ctx *ctx, int buf, const double *dev_from_left,
+                      const double *dev_from_right);
+
+/* -- tuning ------------------------------------------------------------------------------
+ * Tile shapes of the TMA variant.  Keys: "x_tr" (rows per x tile: 4|8), "x_p" (passes of 32
+ * interfaces per x tile row, 2..7; a tile owns 32*x_p-1 cells per row), "z_cfg" (index into
+ * the built-in list of z tile shapes {rows, cols, rows-per-thread}). */
+int pmw_set_tuning(pmw_ctx *ctx, const char *key, int value);
+int pmw_get_tuning(pmw_ctx *ctx, const char *key, int *value);
+
+/* -- introspection ------------------------------------------------------------------ */
+/* Device address / geometry of a logical buffer (for torch-owned views and tests):
+ * element (v,k,i) of the reference layout lives at base[v*vstride + k*pitch + i]. */
+int pmw_buffer_info(pmw_ctx *ctx, int buf, void **base, size_t *pitch, size_t *vstride);
+/* Number of kernels this context has launched since creation (bench.py: gpu_launches). */
+long long pmw_launch_count(pmw_ctx *ctx);
+/* Per-launch device timing of the stage kernels: enable, run, then read the mean duration
+ * in milliseconds and the number of launches timed.  Uses CUDA events on the context stream. */
+int pmw_stage_timing(pmw_ctx *ctx, int enable);
+int pmw_stage_timing_read(pmw_ctx *ctx, double *mean_ms, long long *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMW_H_ */

@@ -1,0 +1,79 @@
+"""Shared plumbing of the operator modules: resolve which device context serves a call.
+
+Two kinds of ``fields`` objects are accepted everywhere:
+
+* ``pyminiweather_b200.data.Fields``  -- device-resident ("lazy") mode: host arrays are
+  refreshed only when read;
+* any other object with the reference's attribute names (e.g. the reference's own
+  ``pyminiweather.data.Fields`` dataclass holding NumPy arrays) -- strict drop-in mode: every
+  call uploads its inputs and downloads its outputs, so the host arrays behave exactly as
+  under the reference's NumPy backend (interior cells; see DESIGN.md on halo cells).
+"""
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+
+from ._lib import PMW_BUF_STATE, PMW_BUF_TMP, PMW_DIR_X, PMW_DIR_Z
+from .data.fields import Fields
+from .engine import HYDRO_NAMES, DeviceSolver
+
+_foreign: dict[int, tuple] = {}
+
+UNSUPPORTED_ICS = ("injection", "gravity")
+
+
+def check_ic(ic_type):
+    """The injection inflow BC (bcs.py:37,41-64) and the gravity-wave source term
+    (source.py:20-50) are not part of the accelerated path yet."""
+    if ic_type in UNSUPPORTED_ICS:
+        raise NotImplementedError(
+            f"ic_type={ic_type!r} is not supported by the B200 hot path (periodic-x / solid-wall-z "
+            "configurations only: thermal, collision, density-current)")
+
+
+def direction_id(direction) -> int:
+    """Accepts the reference's Directions enum (X=1, Z=2), ours, ints or 'x'/'z'."""
+    v = getattr(direction, "value", direction)
+    if isinstance(v, str):
+        v = {"x": PMW_DIR_X, "z": PMW_DIR_Z}[v.lower()]
+    if v not in (PMW_DIR_X, PMW_DIR_Z):
+        raise ValueError(f"unknown direction {direction!r}")
+    return int(v)
+
+
+def is_native(fields) -> bool:
+    return isinstance(fields, Fields)
+
+
+def foreign_solver(fields, params) -> DeviceSolver:
+    """Context cached per foreign fields object (strict mode)."""
+    key = (int(params["nx"]), int(params["nz"]), int(params["hs"]), float(params["dx"]),
+           float(params["dz"]), float(params["dt"]))
+    ent = _foreign.get(id(fields))
+    if ent is None or ent[0] != key or ent[2]() is not fields:
+        if ent is not None:
+            ent[1].close()
+        solver = DeviceSolver(key[0], key[1], key[3], key[4], key[5], hs=key[2])
+        ref = weakref.ref(fields, lambda _r, i=id(fields): _drop(i))
+        ent = (key, solver, ref)
+        _foreign[id(fields)] = ent
+    solver = ent[1]
+    hydro = [np.ascontiguousarray(getattr(fields, n), dtype=np.float64) for n in HYDRO_NAMES]
+    if not solver.hydro_matches(hydro):
+        solver.set_hydrostatic(*hydro)
+    return solver
+
+
+def _drop(i):
+    ent = _foreign.pop(i, None)
+    if ent is not None:
+        ent[1].close()
+
+
+def writable_f64(arr, shape, name):
+    if not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.flags.c_contiguous
+            and arr.flags.writeable and tuple(arr.shape) == tuple(shape)):
+        raise ValueError(f"{name} must be a writable C-contiguous float64 array of shape {tuple(shape)}")
+    return arr

@@ -1,0 +1,785 @@
+// C ABI of libpmw.so (see include/pmw.h): context, data movement, kernel dispatch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pmw.h"
+#include "pmw_aux.cuh"
+#include "pmw_direct.cuh"
+#include "pmw_tma.cuh"
+
+using namespace pmw;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(PMW_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                \
+    } while (0)
+
+#define NEED(cond, ...)                                 \
+    do {                                                \
+        if (!(cond)) return fail(PMW_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+struct TmapKey {
+    int buf, bw, bh;
+    CUtensorMap map;
+};
+
+struct ZCfg { int tr, tc, rpt; };
+static const ZCfg kZCfgs[] = {{32, 32, 8}, {16, 64, 8}, {16, 64, 4}, {16, 32, 8}, {32, 64, 16}, {8, 64, 8}, {8, 128, 8}};
+static const int kNumZCfgs = sizeof(kZCfgs) / sizeof(kZCfgs[0]);
+
+struct pmw_ctx {
+    pmw_params p;
+    Layout L;
+    size_t buf_doubles;
+    double* alloc[3];
+    double* base[3];
+    int l2p[2];  // logical (STATE, TMP) -> physical buffer
+    int spare;
+    bool xhalo_valid[3];  // x halo columns hold the periodic image of the interior
+    double* hydro_blob;
+    Hydro hy;
+    bool hydro_set;
+    cudaStream_t stream;
+    int reverse;
+    // tuning
+    int x_tr, x_p, z_cfg;
+    // tensor maps
+    EncodeTiledFn encode;
+    std::vector<TmapKey> tmaps;
+    // stats scratch
+    double* stats_partial;
+    double* stats_out;
+    int stats_blocks;
+    // bookkeeping
+    long long launches;
+    bool timing;
+    std::vector<cudaEvent_t> ev;  // pairs
+    size_t ev_used;
+};
+
+static int bind(pmw_ctx* c)
+{
+    if (!c) return fail(PMW_EINVAL, "null context");
+    CU_TRY(cudaSetDevice(c->p.device));
+    return PMW_OK;
+}
+#define BIND(c)                   \
+    do {                          \
+        int rc_ = bind(c);        \
+        if (rc_ != PMW_OK) return rc_; \
+    } while (0)
+
+extern "C" const char* pmw_last_error(void) { return g_err; }
+extern "C" int pmw_version(void) { return 100; }
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// best number of 32-interface passes per x tile: fewest wasted cells, then the widest tile
+static int pick_x_passes(int nx)
+{
+    int best = 4;
+    double best_eff = -1.0;
+    for (int p = 2; p <= 7; ++p) {
+        const int tc = 32 * p - 1;
+        const int tiles = (nx + tc - 1) / tc;
+        const double eff = (double)nx / ((double)tiles * tc);
+        if (eff > best_eff + 1e-9 || (fabs(eff - best_eff) <= 1e-9 && p > best && p <= 5)) {
+            best_eff = eff;
+            best = p;
+        }
+    }
+    return best;
+}
+
+extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
+{
+    NEED(params && out, "pmw_create: null argument");
+    NEED(params->hs == HS, "pmw_create: hs must be 2 (got %d)", params->hs);
+    NEED(params->nx >= 4 && params->nz >= 4, "pmw_create: nx and nz must be >= 4 (got %d x %d)", params->nx,
+         params->nz);
+    NEED(params->dx > 0 && params->dz > 0 && params->dt > 0, "pmw_create: dx, dz, dt must be positive");
+    NEED(params->variant == PMW_VARIANT_DIRECT || params->variant == PMW_VARIANT_TMA,
+         "pmw_create: unknown variant %d", params->variant);
+    NEED(params->pow_mode == PMW_POW_LIBDEVICE || params->pow_mode == PMW_POW_BACKGROUND,
+         "pmw_create: unknown pow_mode %d", params->pow_mode);
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    NEED(params->device >= 0 && params->device < ndev, "pmw_create: device %d out of range (%d visible)",
+         params->device, ndev);
+    CU_TRY(cudaSetDevice(params->device));
+
+    pmw_ctx* c = new (std::nothrow) pmw_ctx();
+    if (!c) return fail(PMW_EINVAL, "out of host memory");
+    c->p = *params;
+    c->L.nx = params->nx;
+    c->L.nz = params->nz;
+    c->L.pitch = round_up(LPAD + params->nx + 2 * HS, 16);
+    c->L.vstride = (long long)c->L.pitch * (params->nz + 2 * HS);
+    c->buf_doubles = (size_t)NVAR * c->L.vstride + 32;
+    for (int b = 0; b < 3; ++b) c->alloc[b] = nullptr;
+    c->hydro_blob = nullptr;
+    c->stats_partial = c->stats_out = nullptr;
+    for (int b = 0; b < 3; ++b) {
+        cudaError_t e = cudaMalloc(&c->alloc[b], c->buf_doubles * sizeof(double));
+        if (e != cudaSuccess) {
+            pmw_destroy(c);
+            return fail(PMW_ECUDA, "cudaMalloc of %zu bytes failed: %s", c->buf_doubles * sizeof(double),
+                        cudaGetErrorString(e));
+        }
+        cudaMemset(c->alloc[b], 0, c->buf_doubles * sizeof(double));
+        c->base[b] = c->alloc[b] + LPAD;
+        c->xhalo_valid[b] = false;
+    }
+    c->l2p[PMW_BUF_STATE] = 0;
+    c->l2p[PMW_BUF_TMP] = 1;
+    c->spare = 2;
+    c->hydro_set = false;
+    c->stream = 0;
+    c->reverse = 0;
+    c->x_tr = 8;
+    c->x_p = pick_x_passes(params->nx);
+    c->z_cfg = 1;
+    c->encode = nullptr;
+    c->launches = 0;
+    c->timing = false;
+    c->ev_used = 0;
+    c->stats_blocks = 148 * 8;
+    {
+        const size_t nhy = (size_t)4 * (params->nz + 4) + (size_t)4 * (params->nz + 1);
+        if (cudaMalloc(&c->hydro_blob, nhy * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&c->stats_partial, (size_t)2 * c->stats_blocks * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess) {
+            pmw_destroy(c);
+            return fail(PMW_ECUDA, "cudaMalloc of auxiliary buffers failed");
+        }
+    }
+    if (params->variant == PMW_VARIANT_TMA) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            pmw_destroy(c);
+            return fail(PMW_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+        }
+        c->encode = (EncodeTiledFn)fn;
+    }
+    *out = c;
+    return PMW_OK;
+}
+
+extern "C" int pmw_destroy(pmw_ctx* c)
+{
+    if (!c) return PMW_OK;
+    cudaSetDevice(c->p.device);
+    for (int b = 0; b < 3; ++b)
+        if (c->alloc[b]) cudaFree(c->alloc[b]);
+    if (c->hydro_blob) cudaFree(c->hydro_blob);
+    if (c->stats_partial) cudaFree(c->stats_partial);
+    if (c->stats_out) cudaFree(c->stats_out);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    delete c;
+    return PMW_OK;
+}
+
+extern "C" int pmw_set_stream(pmw_ctx* c, void* s)
+{
+    BIND(c);
+    c->stream = (cudaStream_t)s;
+    return PMW_OK;
+}
+
+extern "C" int pmw_synchronize(pmw_ctx* c)
+{
+    BIND(c);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return PMW_OK;
+}
+
+extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
+{
+    BIND(c);
+    NEED(key, "pmw_set_tuning: null key");
+    if (!strcmp(key, "x_tr")) {
+        NEED(value == 4 || value == 8, "x_tr must be 4 or 8");
+        c->x_tr = value;
+    } else if (!strcmp(key, "x_p")) {
+        NEED(value >= 2 && value <= 7, "x_p must be in 2..7");
+        c->x_p = value;
+    } else if (!strcmp(key, "z_cfg")) {
+        NEED(value >= 0 && value < kNumZCfgs, "z_cfg must be in 0..%d", kNumZCfgs - 1);
+        c->z_cfg = value;
+    } else {
+        return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
+    }
+    return PMW_OK;
+}
+
+extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
+{
+    BIND(c);
+    NEED(key && value, "pmw_get_tuning: null argument");
+    if (!strcmp(key, "x_tr")) *value = c->x_tr;
+    else if (!strcmp(key, "x_p")) *value = c->x_p;
+    else if (!strcmp(key, "z_cfg")) *value = c->z_cfg;
+    else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
+    return PMW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// data movement
+// ---------------------------------------------------------------------------------------------
+extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const double* dens_theta_cell,
+                                   const double* dens_int, const double* dens_theta_int,
+                                   const double* pressure_int)
+{
+    BIND(c);
+    NEED(dens_cell && dens_theta_cell && dens_int && dens_theta_int && pressure_int,
+         "pmw_set_hydrostatic: null profile");
+    const int ncell = c->p.nz + 4, nint = c->p.nz + 1;
+    std::vector<double> h((size_t)4 * ncell + (size_t)4 * nint);
+    double* q = h.data();
+    double* o_dc = q;            q += ncell;
+    double* o_dtc = q;           q += ncell;
+    double* o_idtc = q;          q += ncell;
+    double* o_pc = q;            q += ncell;
+    double* o_di = q;            q += nint;
+    double* o_dti = q;           q += nint;
+    double* o_pi = q;            q += nint;
+    double* o_idti = q;
+    for (int k = 0; k < ncell; ++k) {
+        NEED(dens_cell[k] > 0 && dens_theta_cell[k] > 0, "pmw_set_hydrostatic: non-positive cell profile at %d", k);
+        o_dc[k] = dens_cell[k];
+        o_dtc[k] = dens_theta_cell[k];
+        o_idtc[k] = 1.0 / dens_theta_cell[k];
+        o_pc[k] = C0 * std::pow(dens_theta_cell[k], GAMMA);
+    }
+    for (int k = 0; k < nint; ++k) {
+        NEED(dens_int[k] > 0 && dens_theta_int[k] > 0, "pmw_set_hydrostatic: non-positive interface profile at %d", k);
+        o_di[k] = dens_int[k];
+        o_dti[k] = dens_theta_int[k];
+        o_pi[k] = pressure_int[k];
+        o_idti[k] = 1.0 / dens_theta_int[k];
+    }
+    CU_TRY(cudaMemcpyAsync(c->hydro_blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    double* d = c->hydro_blob;
+    c->hy.dens_cell = d;                d += ncell;
+    c->hy.dens_theta_cell = d;          d += ncell;
+    c->hy.inv_dens_theta_cell = d;      d += ncell;
+    c->hy.pressure_cell = d;            d += ncell;
+    c->hy.dens_int = d;                 d += nint;
+    c->hy.dens_theta_int = d;           d += nint;
+    c->hy.pressure_int = d;             d += nint;
+    c->hy.inv_dens_theta_int = d;
+    c->hydro_set = true;
+    return PMW_OK;
+}
+
+static int check_buf(int buf)
+{
+    if (buf != PMW_BUF_STATE && buf != PMW_BUF_TMP) return fail(PMW_EINVAL, "unknown buffer id %d", buf);
+    return PMW_OK;
+}
+#define CHECK_BUF(b)              \
+    do {                          \
+        int rc_ = check_buf(b);   \
+        if (rc_ != PMW_OK) return rc_; \
+    } while (0)
+
+static int copy_state(pmw_ctx* c, int buf, double* host, bool to_device, bool sync)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(host, "null host pointer");
+    const size_t NX = c->p.nx + 4, rows = (size_t)NVAR * (c->p.nz + 4);
+    double* dev = c->base[c->l2p[buf]];
+    if (to_device) {
+        CU_TRY(cudaMemcpy2DAsync(dev, c->L.pitch * sizeof(double), host, NX * sizeof(double), NX * sizeof(double),
+                                 rows, cudaMemcpyHostToDevice, c->stream));
+        c->xhalo_valid[c->l2p[buf]] = false;
+    } else {
+        CU_TRY(cudaMemcpy2DAsync(host, NX * sizeof(double), dev, c->L.pitch * sizeof(double), NX * sizeof(double),
+                                 rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (sync) CU_TRY(cudaStreamSynchronize(c->stream));
+    return PMW_OK;
+}
+
+extern "C" int pmw_upload_state(pmw_ctx* c, int buf, const double* host)
+{
+    return copy_state(c, buf, const_cast<double*>(host), true, true);
+}
+extern "C" int pmw_download_state(pmw_ctx* c, int buf, double* host) { return copy_state(c, buf, host, false, true); }
+extern "C" int pmw_upload_state_async(pmw_ctx* c, int buf, const double* host)
+{
+    return copy_state(c, buf, const_cast<double*>(host), true, false);
+}
+extern "C" int pmw_download_state_async(pmw_ctx* c, int buf, double* host)
+{
+    return copy_state(c, buf, host, false, false);
+}
+
+extern "C" int pmw_buffer_info(pmw_ctx* c, int buf, void** base, size_t* pitch, size_t* vstride)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    if (base) *base = c->base[c->l2p[buf]];
+    if (pitch) *pitch = (size_t)c->L.pitch;
+    if (vstride) *vstride = (size_t)c->L.vstride;
+    return PMW_OK;
+}
+
+extern "C" long long pmw_launch_count(pmw_ctx* c) { return c ? c->launches : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+static int after_launch(pmw_ctx* c, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PMW_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    c->launches++;
+    return PMW_OK;
+}
+#define LAUNCHED(c, what)                  \
+    do {                                   \
+        int rc_ = after_launch(c, what);   \
+        if (rc_ != PMW_OK) return rc_;     \
+    } while (0)
+
+extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    const int n = NVAR * c->p.nz;
+    bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L);
+    LAUNCHED(c, "bc_x_kernel");
+    c->xhalo_valid[c->l2p[buf]] = true;
+    return PMW_OK;
+}
+
+extern "C" int pmw_bc_z(pmw_ctx* c, int buf)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(c->hydro_set, "pmw_bc_z: hydrostatic profiles not set");
+    const int n = c->p.nx + 4;
+    bc_z_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, c->hy.dens_cell);
+    LAUNCHED(c, "bc_z_kernel");
+    return PMW_OK;
+}
+
+static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** out)
+{
+    for (const TmapKey& k : c->tmaps)
+        if (k.buf == pbuf && k.bw == bw && k.bh == bh) {
+            *out = &k.map;
+            return PMW_OK;
+        }
+    if (c->tmaps.capacity() < 64) c->tmaps.reserve(64);  // keep returned pointers stable
+    NEED(c->tmaps.size() < 64, "tensor-map cache full");
+    TmapKey k;
+    k.buf = pbuf; k.bw = bw; k.bh = bh;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(c->p.nx + 4), (cuuint64_t)(c->p.nz + 4), (cuuint64_t)NVAR};
+    const cuuint64_t gstride[2] = {(cuuint64_t)c->L.pitch * sizeof(double), (cuuint64_t)c->L.vstride * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)NVAR};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = c->encode(&k.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->base[pbuf], gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(PMW_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (box %dx%dx4)", (int)r, bw, bh);
+    c->tmaps.push_back(k);
+    *out = &c->tmaps.back().map;
+    return PMW_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes)
+{
+    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PMW_OK;
+}
+
+template <int TR, int P>
+static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
+{
+    using T = XTile<TR, P>;
+    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + TR - 1) / TR);
+    const size_t smem = T::smem_bytes(has_init);
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+#define GO(HI, PM)                                                                   \
+    do {                                                                             \
+        static unsigned long long attr_done = 0; /* one bit per device */             \
+        if (!(attr_done >> c->p.device & 1ull)) {                                    \
+            int rc_ = set_smem(stage_x_tma<TR, P, HI, PM>, T::smem_bytes(true));     \
+            if (rc_ != PMW_OK) return rc_;                                           \
+            attr_done |= 1ull << c->p.device;                                        \
+        }                                                                            \
+        stage_x_tma<TR, P, HI, PM><<<grid, T::THREADS, smem, c->stream>>>(tf, ti, a); \
+    } while (0)
+    if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
+    else          { if (fast) GO(false, 1); else GO(false, 0); }
+#undef GO
+    return PMW_OK;
+}
+
+template <int TR, int TC, int RPT>
+static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
+{
+    using T = ZTile<TR, TC, RPT>;
+    const dim3 grid((c->p.nx + TC - 1) / TC, (c->p.nz + TR - 1) / TR);
+    const size_t smem = T::smem_bytes(has_init);
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+#define GO(HI, PM)                                                                         \
+    do {                                                                                   \
+        static unsigned long long attr_done = 0; /* one bit per device */                   \
+        if (!(attr_done >> c->p.device & 1ull)) {                                          \
+            int rc_ = set_smem(stage_z_tma<TR, TC, RPT, HI, PM>, T::smem_bytes(true));     \
+            if (rc_ != PMW_OK) return rc_;                                                 \
+            attr_done |= 1ull << c->p.device;                                              \
+        }                                                                                  \
+        stage_z_tma<TR, TC, RPT, HI, PM><<<grid, T::THREADS, smem, c->stream>>>(tf, ti, a); \
+    } while (0)
+    if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
+    else          { if (fast) GO(false, 1); else GO(false, 0); }
+#undef GO
+    return PMW_OK;
+}
+
+template <int TR>
+static int dispatch_x_p(pmw_ctx* c, bool hi, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
+{
+    switch (c->x_p) {
+        case 2: return launch_x_tma<TR, 2>(c, hi, tf, ti, a);
+        case 3: return launch_x_tma<TR, 3>(c, hi, tf, ti, a);
+        case 4: return launch_x_tma<TR, 4>(c, hi, tf, ti, a);
+        case 5: return launch_x_tma<TR, 5>(c, hi, tf, ti, a);
+        case 6: return launch_x_tma<TR, 6>(c, hi, tf, ti, a);
+        case 7: return launch_x_tma<TR, 7>(c, hi, tf, ti, a);
+    }
+    return fail(PMW_EINVAL, "bad x_p %d", c->x_p);
+}
+
+// One fused stage on PHYSICAL buffers.
+static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, int p_out, double dt_stage,
+                        bool write_xhalo, bool fuse_bc_z)
+{
+    NEED(c->hydro_set, "stage: hydrostatic profiles not set (pmw_set_hydrostatic)");
+    NEED(p_out != p_forcing, "internal: stage output aliases the stencil input");
+    StageArgs a;
+    a.L = c->L;
+    a.forcing = c->base[p_forcing];
+    a.init = c->base[p_init];
+    a.out = c->base[p_out];
+    a.out_left = a.out;  // single slab: periodic wrap onto itself
+    a.out_right = a.out;
+    a.hy = c->hy;
+    const double d = (direction == PMW_DIR_X) ? c->p.dx : c->p.dz;
+    a.hv_coeff = -HV_BETA * d / (16 * c->p.dt);
+    a.inv_d = 1.0 / d;
+    a.dt_stage = dt_stage;
+    a.write_xhalo = (write_xhalo && c->p.periodic_x) ? 1 : 0;
+    a.fuse_bc_z = fuse_bc_z ? 1 : 0;
+    const bool has_init = (p_init != p_forcing);
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {
+        if (c->ev_used + 2 > c->ev.size()) {
+            for (int n = 0; n < 2; ++n) {
+                cudaEvent_t e;
+                CU_TRY(cudaEventCreate(&e));
+                c->ev.push_back(e);
+            }
+        }
+        e0 = c->ev[c->ev_used];
+        e1 = c->ev[c->ev_used + 1];
+        c->ev_used += 2;
+        CU_TRY(cudaEventRecord(e0, c->stream));
+    }
+
+    if (c->p.variant == PMW_VARIANT_DIRECT) {
+        const dim3 block(64, 4);
+        const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4);
+        const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+        if (direction == PMW_DIR_X) {
+            if (fast) stage_x_direct<1><<<grid, block, 0, c->stream>>>(a);
+            else stage_x_direct<0><<<grid, block, 0, c->stream>>>(a);
+        } else {
+            if (fast) stage_z_direct<1><<<grid, block, 0, c->stream>>>(a);
+            else stage_z_direct<0><<<grid, block, 0, c->stream>>>(a);
+        }
+    } else {
+        const CUtensorMap *tf = nullptr, *ti = nullptr;
+        int rc;
+        if (direction == PMW_DIR_X) {
+            const int fw = 32 * c->x_p + 4, iw = 32 * c->x_p;
+            if ((rc = get_tmap(c, p_forcing, fw, c->x_tr, &tf)) != PMW_OK) return rc;
+            if ((rc = get_tmap(c, p_init, iw, c->x_tr, &ti)) != PMW_OK) return rc;
+            rc = (c->x_tr == 4) ? dispatch_x_p<4>(c, has_init, *tf, *ti, a) : dispatch_x_p<8>(c, has_init, *tf, *ti, a);
+            if (rc != PMW_OK) return rc;
+        } else {
+            const ZCfg z = kZCfgs[c->z_cfg];
+            if ((rc = get_tmap(c, p_forcing, z.tc, z.tr + 4, &tf)) != PMW_OK) return rc;
+            if ((rc = get_tmap(c, p_init, z.tc, z.tr, &ti)) != PMW_OK) return rc;
+            switch (c->z_cfg) {
+                case 0: rc = launch_z_tma<32, 32, 8>(c, has_init, *tf, *ti, a); break;
+                case 1: rc = launch_z_tma<16, 64, 8>(c, has_init, *tf, *ti, a); break;
+                case 2: rc = launch_z_tma<16, 64, 4>(c, has_init, *tf, *ti, a); break;
+                case 3: rc = launch_z_tma<16, 32, 8>(c, has_init, *tf, *ti, a); break;
+                case 4: rc = launch_z_tma<32, 64, 16>(c, has_init, *tf, *ti, a); break;
+                case 5: rc = launch_z_tma<8, 64, 8>(c, has_init, *tf, *ti, a); break;
+                case 6: rc = launch_z_tma<8, 128, 8>(c, has_init, *tf, *ti, a); break;
+                default: rc = fail(PMW_EINVAL, "bad z_cfg");
+            }
+            if (rc != PMW_OK) return rc;
+        }
+    }
+    LAUNCHED(c, direction == PMW_DIR_X ? "x stage kernel" : "z stage kernel");
+    if (c->timing) CU_TRY(cudaEventRecord(e1, c->stream));
+    c->xhalo_valid[p_out] = a.write_xhalo != 0;
+    return PMW_OK;
+}
+
+extern "C" int pmw_stage(pmw_ctx* c, int direction, int init_buf, int forcing_buf, int out_buf, double dt_stage)
+{
+    BIND(c);
+    CHECK_BUF(init_buf);
+    CHECK_BUF(forcing_buf);
+    CHECK_BUF(out_buf);
+    NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_stage: bad direction %d", direction);
+    const int p_init = c->l2p[init_buf], p_forcing = c->l2p[forcing_buf];
+    if (out_buf == forcing_buf) {
+        // step.py:122-131: the update overwrites the array the stencil reads.  NumPy materialises
+        // the tendency first; here the result goes to the spare buffer, which then becomes `out`
+        // (with the halo ring the in-place array would still carry).
+        const int p_out = c->spare;
+        int rc = launch_stage(c, direction, p_init, p_forcing, p_out, dt_stage, false, false);
+        if (rc != PMW_OK) return rc;
+        const int n = NVAR * (4 * (c->p.nx + 4) + 4 * c->p.nz);
+        copy_halo_ring_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[p_out], c->base[p_forcing], c->L);
+        LAUNCHED(c, "copy_halo_ring_kernel");
+        c->xhalo_valid[p_out] = false;  // the ring is the image of the OLD interior, as in the reference
+        c->l2p[out_buf] = p_out;
+        c->spare = p_forcing;
+        return PMW_OK;
+    }
+    // the halo of `out` is untouched by the update (step.py:80-82) while its interior changes,
+    // so it stops being the periodic image (launch_stage records that)
+    return launch_stage(c, direction, p_init, p_forcing, c->l2p[out_buf], dt_stage, false, false);
+}
+
+extern "C" int pmw_discrete_step(pmw_ctx* c, int direction, int init_buf, int forcing_buf, int out_buf,
+                                 double dt_stage)
+{
+    int rc = (direction == PMW_DIR_X) ? pmw_bc_x(c, forcing_buf) : pmw_bc_z(c, forcing_buf);
+    if (rc != PMW_OK) return rc;
+    return pmw_stage(c, direction, init_buf, forcing_buf, out_buf, dt_stage);
+}
+
+// One RK stage of the fused time step, with the three-buffer rotation:
+//   stage 1: TMP   <- STATE + dt/3 * T(STATE)
+//   stage 2: spare <- STATE + dt/2 * T(TMP);  TMP := spare
+//   stage 3: STATE <- STATE + dt   * T(TMP)   (in place: init is only read at the written cell)
+extern "C" int pmw_evolve_stage(pmw_ctx* c, int direction, int rk_stage, double dt)
+{
+    BIND(c);
+    NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_evolve_stage: bad direction %d", direction);
+    NEED(rk_stage >= 1 && rk_stage <= 3, "pmw_evolve_stage: rk_stage must be 1..3");
+    if (dt <= 0) dt = c->p.dt;
+    const int S = c->l2p[PMW_BUF_STATE], T = c->l2p[PMW_BUF_TMP];
+    const int p_forcing = (rk_stage == 1) ? S : T;
+    if (direction == PMW_DIR_X && !c->xhalo_valid[p_forcing]) {
+        NEED(c->p.periodic_x, "pmw_evolve_stage: x halos of the forcing buffer are stale; a slab context "
+                              "needs pmw_unpack_halo_x (neighbour columns) before every x stage");
+        const int n = NVAR * c->p.nz;
+        bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[p_forcing], c->L);
+        LAUNCHED(c, "bc_x_kernel");
+        c->xhalo_valid[p_forcing] = true;
+    }
+    int rc;
+    if (rk_stage == 1) {
+        rc = launch_stage(c, direction, S, S, T, dt / 3, true, true);
+    } else if (rk_stage == 2) {
+        rc = launch_stage(c, direction, S, T, c->spare, dt / 2, true, true);
+        if (rc == PMW_OK) {
+            c->l2p[PMW_BUF_TMP] = c->spare;
+            c->spare = T;
+        }
+    } else {
+        rc = launch_stage(c, direction, S, T, S, dt / 1, true, true);
+    }
+    return rc;
+}
+
+extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
+{
+    BIND(c);
+    NEED(nsteps >= 0, "pmw_evolve: negative nsteps");
+    NEED(c->p.periodic_x, "pmw_evolve: a slab context (periodic_x=0) must be stepped stage by stage "
+                          "with pmw_evolve_stage and a halo exchange before every x stage");
+    for (int n = 0; n < nsteps; ++n) {
+        const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
+        for (int d = 0; d < 2; ++d)
+            for (int s = 1; s <= 3; ++s) {
+                int rc = pmw_evolve_stage(c, dirs[d], s, dt);
+                if (rc != PMW_OK) return rc;
+            }
+        c->reverse = !c->reverse;
+    }
+    return PMW_OK;
+}
+
+extern "C" int pmw_get_reverse_direction(pmw_ctx* c, int* reverse)
+{
+    BIND(c);
+    NEED(reverse, "null pointer");
+    *reverse = c->reverse;
+    return PMW_OK;
+}
+extern "C" int pmw_set_reverse_direction(pmw_ctx* c, int reverse)
+{
+    BIND(c);
+    c->reverse = reverse ? 1 : 0;
+    return PMW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------
+extern "C" int pmw_stats_device(pmw_ctx* c, int buf, double* dev_out2)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(dev_out2, "pmw_stats_device: null output");
+    NEED(c->hydro_set, "pmw_stats: hydrostatic profiles not set");
+    stats_partial_kernel<<<c->stats_blocks, 256, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, c->hy.dens_cell,
+                                                                c->hy.dens_theta_cell, c->stats_partial);
+    LAUNCHED(c, "stats_partial_kernel");
+    stats_final_kernel<<<1, 256, 0, c->stream>>>(c->stats_partial, c->stats_blocks, c->p.dx * c->p.dz, dev_out2);
+    LAUNCHED(c, "stats_final_kernel");
+    return PMW_OK;
+}
+
+extern "C" int pmw_stats(pmw_ctx* c, int buf, double out[2])
+{
+    NEED(out, "pmw_stats: null output");
+    int rc = pmw_stats_device(c, buf, c ? c->stats_out : nullptr);
+    if (rc != PMW_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(out, c->stats_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return PMW_OK;
+}
+
+extern "C" int pmw_solution_variables(pmw_ctx* c, int buf, double* host_out)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(host_out, "pmw_solution_variables: null output");
+    NEED(c->hydro_set, "pmw_solution_variables: hydrostatic profiles not set");
+    const size_t n = (size_t)c->p.nx * c->p.nz;
+    double* dev = nullptr;
+    CU_TRY(cudaMalloc(&dev, 4 * n * sizeof(double)));
+    solution_variables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        c->base[c->l2p[buf]], c->L, c->hy.dens_cell, c->hy.dens_theta_cell, dev);
+    int rc = after_launch(c, "solution_variables_kernel");
+    if (rc == PMW_OK) {
+        cudaError_t e = cudaMemcpyAsync(host_out, dev, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(PMW_ECUDA, "solution variables copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(dev);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// x-slab halo messages
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t pmw_halo_len(pmw_ctx* c) { return c ? (size_t)NVAR * c->p.nz * 2 : 0; }
+
+extern "C" int pmw_pack_halo_x(pmw_ctx* c, int buf, double* to_left, double* to_right)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(to_left && to_right, "pmw_pack_halo_x: null message buffer");
+    const int n = NVAR * c->p.nz * 2;
+    pack_halo_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, to_left, to_right);
+    LAUNCHED(c, "pack_halo_x_kernel");
+    return PMW_OK;
+}
+
+extern "C" int pmw_unpack_halo_x(pmw_ctx* c, int buf, const double* from_left, const double* from_right)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(from_left && from_right, "pmw_unpack_halo_x: null message buffer");
+    const int n = NVAR * c->p.nz * 2;
+    unpack_halo_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, from_left, from_right);
+    LAUNCHED(c, "unpack_halo_x_kernel");
+    c->xhalo_valid[c->l2p[buf]] = true;
+    return PMW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-launch timing of the stage kernels
+// ---------------------------------------------------------------------------------------------
+extern "C" int pmw_stage_timing(pmw_ctx* c, int enable)
+{
+    BIND(c);
+    c->timing = enable != 0;
+    c->ev_used = 0;
+    return PMW_OK;
+}
+
+extern "C" int pmw_stage_timing_read(pmw_ctx* c, double* mean_ms, long long* count)
+{
+    BIND(c);
+    NEED(mean_ms && count, "null pointer");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    double total = 0.0;
+    long long n = 0;
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        total += ms;
+        ++n;
+    }
+    *mean_ms = n ? total / (double)n : 0.0;
+    *count = n;
+    c->ev_used = 0;
+    return PMW_OK;
+}

@@ -1,0 +1,171 @@
+// Halo / boundary-condition kernels, slab halo pack/unpack, and the mass/energy reduction.
+#pragma once
+#include "pmw_common.cuh"
+
+namespace pmw {
+
+// set_bc_x, periodic branch (bcs.py:35-39): interior rows only, all four variables.
+__global__ void bc_x_kernel(double* s, const Layout L)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NVAR * L.nz) return;
+    const int v = t / L.nz, k = t % L.nz + HS;
+    double* row = s + idx(L, v, k, 0);
+    const int nx = L.nx;
+    row[0] = row[nx];
+    row[1] = row[nx + 1];
+    row[nx + HS] = row[HS];
+    row[nx + HS + 1] = row[HS + 1];
+}
+
+// set_bc_z (bcs.py:92-148): all nx+4 columns.  True divisions, in the reference's order.
+__global__ void bc_z_kernel(double* s, const Layout L, const double* __restrict__ hd)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nx + 2 * HS) return;
+    const int nz = L.nz, top = nz + HS - 1;
+    const double hb = hd[HS], ht = hd[top];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        s[idx(L, WMOM, j, i)] = 0.0;
+        s[idx(L, WMOM, nz + HS + j, i)] = 0.0;
+        s[idx(L, UMOM, j, i)] = s[idx(L, UMOM, HS, i)] / hb * hd[j];
+        s[idx(L, UMOM, nz + HS + j, i)] = s[idx(L, UMOM, top, i)] / ht * hd[nz + HS + j];
+        s[idx(L, DENS, j, i)] = s[idx(L, DENS, HS, i)];
+        s[idx(L, DENS, nz + HS + j, i)] = s[idx(L, DENS, top, i)];
+        s[idx(L, RHOT, j, i)] = s[idx(L, RHOT, HS, i)];
+        s[idx(L, RHOT, nz + HS + j, i)] = s[idx(L, RHOT, top, i)];
+    }
+}
+
+// Copies the halo ring (2 rows top/bottom over all columns, 2 columns left/right over the
+// interior rows) from src to dst.  Used by pmw_stage when `out` aliases `forcing`
+// (step.py:122-131): the update is written to the spare buffer, which then takes over the
+// role of `out`; its halo must be the one the reference's in-place array would still hold.
+__global__ void copy_halo_ring_kernel(double* dst, const double* __restrict__ src, const Layout L)
+{
+    const int NX = L.nx + 2 * HS, NZ = L.nz + 2 * HS;
+    const int per_var = 4 * NX + 4 * L.nz;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NVAR * per_var) return;
+    const int v = t / per_var;
+    int e = t % per_var, k, i;
+    if (e < 4 * NX) {
+        const int r = e / NX;
+        k = (r < 2) ? r : NZ - 4 + r;
+        i = e % NX;
+    } else {
+        e -= 4 * NX;
+        const int c = e % 4;
+        k = e / 4 + HS;
+        i = (c < 2) ? c : NX - 4 + c;
+    }
+    dst[idx(L, v, k, i)] = src[idx(L, v, k, i)];
+}
+
+// Slab halo exchange messages: [4][nz][2] doubles each (set_bc_x generalised to a ring of
+// slabs).  to_left = first two interior columns, to_right = last two.
+__global__ void pack_halo_x_kernel(const double* __restrict__ s, const Layout L, double* to_left,
+                                   double* to_right)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NVAR * L.nz * 2) return;
+    const int j = t & 1, k = (t >> 1) % L.nz, v = (t >> 1) / L.nz;
+    to_left[t] = s[idx(L, v, k + HS, HS + j)];
+    to_right[t] = s[idx(L, v, k + HS, L.nx + j)];
+}
+__global__ void unpack_halo_x_kernel(double* s, const Layout L, const double* __restrict__ from_left,
+                                     const double* __restrict__ from_right)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NVAR * L.nz * 2) return;
+    const int j = t & 1, k = (t >> 1) % L.nz, v = (t >> 1) / L.nz;
+    s[idx(L, v, k + HS, j)] = from_left[t];               // left neighbour's last two columns
+    s[idx(L, v, k + HS, L.nx + HS + j)] = from_right[t];  // right neighbour's first two
+}
+
+// ---- compute_stats (stats.py:16-33) ----------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// Pass 1: grid-stride over interior cells, pairwise-ish accumulation (per thread, then
+// warp-shuffle tree, then one partial per block).  partial[2*b] = sum rho, [2*b+1] = sum(ke+ie).
+__global__ void __launch_bounds__(256) stats_partial_kernel(const double* __restrict__ s, const Layout L,
+                                                            const double* __restrict__ hd,
+                                                            const double* __restrict__ hdt,
+                                                            double* partial)
+{
+    const long long n = (long long)L.nx * L.nz;
+    double mass = 0.0, energy = 0.0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(c / L.nx), i = (int)(c % L.nx);
+        const double rho = s[idx(L, DENS, k + HS, i + HS)] + hd[k + HS];
+        const double u = s[idx(L, UMOM, k + HS, i + HS)] / rho;
+        const double w = s[idx(L, WMOM, k + HS, i + HS)] / rho;
+        const double th = (s[idx(L, RHOT, k + HS, i + HS)] + hdt[k + HS]) / rho;
+        const double p = C0 * pow(rho * th, GAMMA);
+        const double t = th / pow(P0 / p, RD / CP);
+        mass += rho;
+        energy += rho * (u * u + w * w) + rho * CV * t;  // no 1/2 on the kinetic term (stats.py:27)
+    }
+    __shared__ double sm[2][8];
+    mass = warp_sum(mass);
+    energy = warp_sum(energy);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sm[0][warp] = mass; sm[1][warp] = energy; }
+    __syncthreads();
+    if (warp == 0) {
+        mass = lane < 8 ? sm[0][lane] : 0.0;
+        energy = lane < 8 ? sm[1][lane] : 0.0;
+        mass = warp_sum(mass);
+        energy = warp_sum(energy);
+        if (lane == 0) { partial[2 * blockIdx.x] = mass; partial[2 * blockIdx.x + 1] = energy; }
+    }
+}
+
+// Pass 2: one block folds the per-block partials in a fixed order and scales by dx*dz.
+__global__ void __launch_bounds__(256) stats_final_kernel(const double* __restrict__ partial, int nblocks,
+                                                          double cell_area, double* out2)
+{
+    double mass = 0.0, energy = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+        mass += partial[2 * b];
+        energy += partial[2 * b + 1];
+    }
+    __shared__ double sm[2][8];
+    mass = warp_sum(mass);
+    energy = warp_sum(energy);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sm[0][warp] = mass; sm[1][warp] = energy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0, e = 0.0;
+        for (int wv = 0; wv < 8; ++wv) { m += sm[0][wv]; e += sm[1][wv]; }
+        out2[0] = m * cell_area;
+        out2[1] = e * cell_area;
+    }
+}
+
+// compute_solution_variables (stats.py:38-69): dense [4][nz][nx] output.
+__global__ void solution_variables_kernel(const double* __restrict__ s, const Layout L,
+                                          const double* __restrict__ hd, const double* __restrict__ hdt,
+                                          double* out)
+{
+    const long long n = (long long)L.nx * L.nz;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int k = (int)(c / L.nx), i = (int)(c % L.nx);
+    const double d = s[idx(L, DENS, k + HS, i + HS)];
+    const double rho = hd[k + HS] + d;
+    out[c] = d;
+    out[n + c] = s[idx(L, UMOM, k + HS, i + HS)] / rho;
+    out[2 * n + c] = s[idx(L, WMOM, k + HS, i + HS)] / rho;
+    out[3 * n + c] = (s[idx(L, RHOT, k + HS, i + HS)] + hdt[k + HS]) / rho - hdt[k + HS] / hd[k + HS];
+}
+
+}  // namespace pmw

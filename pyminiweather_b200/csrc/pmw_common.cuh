@@ -1,0 +1,170 @@
+// Shared device-side definitions for the PyMiniWeather hot path on sm_100a.
+//
+// Device layout of one state buffer (chosen for 128-byte aligned interior rows,
+// TMA-legal strides and vector access; the reference's host layout is
+// [4][nz+4][nx+4] dense, pyminiweather/data/fields.py:67-72):
+//
+//     element (v, k, i), i in [0, nx+4)  ->  base[v*vstride + k*pitch + i]
+//
+// where `base` = allocation + LPAD doubles, LPAD = 14, so that the first
+// interior column (i = 2) sits on a 128-byte boundary; pitch is a multiple of
+// 16 doubles (128 B) and vstride = pitch * (nz+4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pmw {
+
+constexpr int HS = 2;
+constexpr int NVAR = 4;
+constexpr int LPAD = 14;
+enum { DENS = 0, UMOM = 1, WMOM = 2, RHOT = 3 };  // pyminiweather/__init__.py:14-18
+
+// pyminiweather/data/constants.py:4-27
+constexpr double HV_BETA = 0.05;
+constexpr double P0 = 1.0e5;
+constexpr double C0 = 27.5629410929725921310572974482;
+constexpr double GAMMA = 1.40027894002789400278940027894;
+constexpr double GRAV = 9.8;
+constexpr double CP = 1004.0;
+constexpr double CV = 717.0;
+constexpr double RD = 287.0;
+
+struct Layout {
+    int nx, nz;       // interior size of this slab
+    int pitch;        // doubles per row
+    long long vstride;  // doubles per variable plane
+};
+
+__host__ __device__ inline long long idx(const Layout& L, int v, int k, int i)
+{
+    return (long long)v * L.vstride + (long long)k * L.pitch + i;
+}
+
+// Hydrostatic background profiles on the device (pyminiweather/ics/initial.py:84-105) plus
+// derived per-row tables for the background-relative pressure evaluation.
+struct Hydro {
+    const double* dens_cell;        // [nz+4]
+    const double* dens_theta_cell;  // [nz+4]
+    const double* dens_int;         // [nz+1]
+    const double* dens_theta_int;   // [nz+1]
+    const double* pressure_int;     // [nz+1]
+    const double* inv_dens_theta_cell;  // [nz+4]  1/dens_theta_cell
+    const double* pressure_cell;        // [nz+4]  C0*dens_theta_cell^gamma
+    const double* inv_dens_theta_int;   // [nz+1]  1/dens_theta_int
+};
+
+struct StageArgs {
+    Layout L;
+    const double* forcing;
+    const double* init;
+    double* out;
+    double* out_left;   // same logical buffer on the left  slab neighbour (== out when periodic_x)
+    double* out_right;  // same logical buffer on the right slab neighbour
+    Hydro hy;
+    double hv_coeff;  // -hv_beta*d/(16*dt_full)   (interpolate.py:101,149)
+    double inv_d;     // 1/dx or 1/dz
+    double dt_stage;
+    int write_xhalo;  // also store the periodic/neighbour images of the edge columns
+    int fuse_bc_z;    // z stages: rebuild the wall halo rows on the fly (set_bc_z folded in)
+};
+
+// ---------------------------------------------------------------------------------
+// (1+e)^gamma - 1 on |e| <= 1/8: degree-12 polynomial (Chebyshev-node interpolant of
+// ((1+e)^gamma-1)/e, truncation error 7e-20, evaluated as two interleaved Horner chains in
+// e^2; absolute error <= 4e-17 measured against mpmath).  Used by PMW_POW_BACKGROUND.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double pow1p_gamma_m1(double e)
+{
+    const double e2 = e * e;
+    double a = -0x1.f04c6e36150e8p-11;        // c12
+    double b = 0x1.300687b793e42p-10;         // c11
+    a = fma(a, e2, -0x1.6efd8124188fdp-10);   // c10
+    b = fma(b, e2, 0x1.d56fc4d94646ap-10);    // c9
+    a = fma(a, e2, -0x1.34fc42d60dfbcp-9);    // c8
+    b = fma(b, e2, 0x1.a55c83fc9dc65p-9);     // c7
+    a = fma(a, e2, -0x1.2cfc9a56ff6c7p-8);    // c6
+    b = fma(b, e2, 0x1.ca0d1259f841dp-8);     // c5
+    a = fma(a, e2, -0x1.7dbd21dc9b33fp-7);    // c4
+    b = fma(b, e2, 0x1.6f188e3a61d00p-6);     // c3
+    a = fma(a, e2, -0x1.caf32d76b8de6p-5);    // c2
+    b = fma(b, e2, 0x1.1efa23f1c08bdp-2);     // c1
+    a = fma(a, e2, 0x1.6678ae3cb2859p+0);     // c0
+    return fma(b, e, a) * e;
+}
+
+// Everything one interface needs besides the 4x4 stencil values.
+struct IfaceBg {
+    double dens;       // hydrostatic density at the interface (x: cell row value)
+    double dens_theta; // hydrostatic rho*theta
+    double inv_dens_theta;
+    double pressure;   // x: C0*dens_theta^gamma of the row;  z: hy_pressure_int[k]
+};
+
+// Interface flux from the four stencil taps of the four variables.
+//   DIR_Z = false: compute_flux_x (interpolate.py:105-129)
+//   DIR_Z = true : compute_flux_z (interpolate.py:153-186), `wall` = (k==0 || k==nz)
+// Interpolation weights: fields.py:94-97 (4th-order value, flipped 3rd difference).
+// Differences from the reference's rounding: FMA contraction, one reciprocal of rho instead
+// of three divisions, optional polynomial pressure -- all validated at <= 1e-12 rel-L2
+// (tools/arith_probe).
+template <bool DIR_Z, int POW_MODE>
+__device__ __forceinline__ void interface_flux(const double (&s0)[4], const double (&s1)[4],
+                                               const double (&s2)[4], const double (&s3)[4],
+                                               const IfaceBg& bg, double hv, bool wall,
+                                               double (&flux)[4])
+{
+    constexpr double c0 = -1.0 / 12, c1 = 7.0 / 12;
+    double val[4], d3[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        val[v] = fma(c0, s3[v], fma(c1, s2[v], fma(c1, s1[v], c0 * s0[v])));
+        d3[v] = fma(-3.0, s2[v], fma(3.0, s1[v], -s0[v])) + s3[v];
+    }
+    const double rho = val[DENS] + bg.dens;
+    const double r = 1.0 / rho;
+    const double u = val[UMOM] * r;
+    double w = val[WMOM] * r;
+    const double t = (val[RHOT] + bg.dens_theta) * r;
+    const double rt = rho * t;
+    double p;  // x: full pressure; z: pressure perturbation p - hy_pressure_int
+    if (POW_MODE == 1) {
+        const double e = (rt - bg.dens_theta) * bg.inv_dens_theta;
+        if (fabs(e) <= 0.125) {
+            const double f = pow1p_gamma_m1(e);
+            p = DIR_Z ? bg.pressure * f : fma(bg.pressure, f, bg.pressure);
+        } else {
+            p = C0 * pow(rt, GAMMA);
+            if (DIR_Z) p -= bg.pressure;
+        }
+    } else {
+        p = C0 * pow(rt, GAMMA);
+        if (DIR_Z) p -= bg.pressure;
+    }
+    if (DIR_Z) {
+        if (wall) { w = 0.0; d3[DENS] = 0.0; }
+        const double rw = rho * w;
+        flux[DENS] = fma(-hv, d3[DENS], rw);
+        flux[UMOM] = fma(-hv, d3[UMOM], rw * u);
+        flux[WMOM] = fma(-hv, d3[WMOM], fma(rho, w * w, p));
+        flux[RHOT] = fma(-hv, d3[RHOT], rw * t);
+    } else {
+        const double ru = rho * u;
+        flux[DENS] = fma(-hv, d3[DENS], ru);
+        flux[UMOM] = fma(-hv, d3[UMOM], fma(rho, u * u, p));
+        flux[WMOM] = fma(-hv, d3[WMOM], ru * w);
+        flux[RHOT] = fma(-hv, d3[RHOT], ru * t);
+    }
+}
+
+// Wall halo value for set_bc_z folded into a z stage (bcs.py:92-148): `interior` is the
+// value of the nearest interior row in the same column, hd_* the hydrostatic densities.
+__device__ __forceinline__ double wall_value(int v, double interior, double hd_interior,
+                                             double hd_halo)
+{
+    if (v == WMOM) return 0.0;
+    if (v == UMOM) return interior / hd_interior * hd_halo;
+    return interior;
+}
+
+}  // namespace pmw

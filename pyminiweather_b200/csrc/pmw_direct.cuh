@@ -1,0 +1,109 @@
+// Variant 0 ("direct"): one thread per cell, stencil operands read straight from global
+// memory through L1/L2, both interface fluxes of the cell recomputed by the owning thread.
+// No shared memory, no inter-thread exchange: it is the simplest correct GPU formulation of a
+// stage and serves as the on-device cross-check of the TMA variant (and as the fallback for
+// grids too small for a tile).  Same arithmetic (interface_flux) as the production kernels.
+#pragma once
+#include "pmw_common.cuh"
+
+namespace pmw {
+
+// Stores one updated cell and, when asked, its periodic / slab-neighbour halo image
+// (set_bc_x, bcs.py:35-39, folded into the producer of the next x stage's forcing state).
+__device__ __forceinline__ void store_cell(const StageArgs& a, int v, int k, int i, double val)
+{
+    const long long o = idx(a.L, v, k + HS, i + HS);
+    a.out[o] = val;
+    if (a.write_xhalo) {
+        if (i < HS) a.out_left[o + a.L.nx] = val;             // left neighbour's right halo
+        if (i >= a.L.nx - HS) a.out_right[o - a.L.nx] = val;  // right neighbour's left halo
+    }
+}
+
+__device__ __forceinline__ IfaceBg bg_x(const Hydro& hy, int krow /* array row */)
+{
+    IfaceBg bg;
+    bg.dens = __ldg(hy.dens_cell + krow);
+    bg.dens_theta = __ldg(hy.dens_theta_cell + krow);
+    bg.inv_dens_theta = __ldg(hy.inv_dens_theta_cell + krow);
+    bg.pressure = __ldg(hy.pressure_cell + krow);
+    return bg;
+}
+
+__device__ __forceinline__ IfaceBg bg_z(const Hydro& hy, int k /* interface */)
+{
+    IfaceBg bg;
+    bg.dens = __ldg(hy.dens_int + k);
+    bg.dens_theta = __ldg(hy.dens_theta_int + k);
+    bg.inv_dens_theta = __ldg(hy.inv_dens_theta_int + k);
+    bg.pressure = __ldg(hy.pressure_int + k);
+    return bg;
+}
+
+// x stage: interpolate_x + compute_flux_x + compute_tend_x + update (step.py:69-71,80-82).
+template <int POW_MODE>
+__global__ void __launch_bounds__(256) stage_x_direct(const StageArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // interior column
+    const int k = blockIdx.y * blockDim.y + threadIdx.y;  // interior row
+    if (i >= a.L.nx || k >= a.L.nz) return;
+    double s[5][4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const double* f = a.forcing + idx(a.L, v, k + HS, i);  // array column i = cell i-2
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s[j][v] = __ldg(f + j);
+    }
+    const IfaceBg bg = bg_x(a.hy, k + HS);
+    double fl[4], fr[4];
+    interface_flux<false, POW_MODE>(s[0], s[1], s[2], s[3], bg, a.hv_coeff, false, fl);
+    interface_flux<false, POW_MODE>(s[1], s[2], s[3], s[4], bg, a.hv_coeff, false, fr);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const double tend = (fl[v] - fr[v]) * a.inv_d;
+        const double ini = (a.init == a.forcing) ? s[2][v] : __ldg(a.init + idx(a.L, v, k + HS, i + HS));
+        store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
+    }
+}
+
+// z stage: interpolate_z + compute_flux_z + compute_tend_z + update (step.py:74-76,80-82).
+template <int POW_MODE>
+__global__ void __launch_bounds__(256) stage_z_direct(const StageArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y;
+    const int nz = a.L.nz;
+    if (i >= a.L.nx || k >= nz) return;
+    double s[5][4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int kk = k + j;  // array row = cell row k-2+j
+            double val;
+            if (a.fuse_bc_z && kk < HS) {
+                val = wall_value(v, __ldg(a.forcing + idx(a.L, v, HS, i + HS)),
+                                 __ldg(a.hy.dens_cell + HS), __ldg(a.hy.dens_cell + kk));
+            } else if (a.fuse_bc_z && kk >= nz + HS) {
+                val = wall_value(v, __ldg(a.forcing + idx(a.L, v, nz + HS - 1, i + HS)),
+                                 __ldg(a.hy.dens_cell + nz + HS - 1), __ldg(a.hy.dens_cell + kk));
+            } else {
+                val = __ldg(a.forcing + idx(a.L, v, kk, i + HS));
+            }
+            s[j][v] = val;
+        }
+    }
+    double fb[4], ft[4];
+    interface_flux<true, POW_MODE>(s[0], s[1], s[2], s[3], bg_z(a.hy, k), a.hv_coeff, k == 0, fb);
+    interface_flux<true, POW_MODE>(s[1], s[2], s[3], s[4], bg_z(a.hy, k + 1), a.hv_coeff,
+                                   k + 1 == nz, ft);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        double tend = (fb[v] - ft[v]) * a.inv_d;
+        if (v == WMOM) tend = fma(-s[2][DENS], GRAV, tend);  // interpolate.py:248-250
+        const double ini = (a.init == a.forcing) ? s[2][v] : __ldg(a.init + idx(a.L, v, k + HS, i + HS));
+        store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
+    }
+}
+
+}  // namespace pmw

@@ -1,0 +1,131 @@
+"""``Fields``: the persistent arrays of one simulation, device-resident.
+
+Mirror of pyminiweather/data/fields.py:7-123.  Attribute names and shapes are the
+reference's; the difference is where the truth lives:
+
+* ``state`` / ``state_tmp`` are properties.  The authoritative copy is in HBM once any
+  operator has run; reading the property pulls it into the (persistent) host array, and --
+  because the caller receives a mutable NumPy array -- marks the host copy as possibly
+  modified so that the next operator pushes it back.  A time loop that only calls
+  ``evolve`` therefore never touches PCIe.
+* the interpolation / flux / tendency scratch arrays (``vals_x`` ... ``tend``,
+  fields.py:70-78) are not used by the fused kernels; they are allocated lazily on first
+  access for code that still wants them (the unfused ``interpolate_*`` shims).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .._lib import PMW_BUF_STATE, PMW_BUF_TMP
+from ..engine import HYDRO_NAMES, DeviceSolver
+
+_LAZY_SHAPES = {
+    "flux": lambda f: (f.nvariables, f.nz + 1, f.nx + 1),
+    "tend": lambda f: (f.nvariables, f.nz, f.nx),
+    "vals_x": lambda f: (f.nvariables, f.nz, f.nx + 1),
+    "d3_vals_x": lambda f: (f.nvariables, f.nz, f.nx + 1),
+    "vals_z": lambda f: (f.nvariables, f.nz + 1, f.nx),
+    "d3_vals_z": lambda f: (f.nvariables, f.nz + 1, f.nx),
+}
+
+
+class Fields:
+    def __init__(self, nx: int, nz: int, hs: int = 2, s: int = 4, nvariables: int = 4):
+        assert hs * 2 - s == 0  # fields.py:65
+        self.nx, self.nz, self.hs, self.s, self.nvariables = nx, nz, hs, s, nvariables
+        self.shape = (nvariables, nz + 2 * hs, nx + 2 * hs)
+        self._host = {PMW_BUF_STATE: np.zeros(self.shape), PMW_BUF_TMP: np.zeros(self.shape)}
+        self._host_dirty = {PMW_BUF_STATE: True, PMW_BUF_TMP: True}
+        self._dev_newer = {PMW_BUF_STATE: False, PMW_BUF_TMP: False}
+        self._solver: DeviceSolver | None = None
+        self._solver_key = None
+        self._lazy = {}
+        # hydrostatic background, 1-D in z (fields.py:80-85)
+        self.hy_dens_cell = np.zeros(nz + 2 * hs)
+        self.hy_dens_theta_cell = np.zeros(nz + 2 * hs)
+        self.hy_dens_int = np.zeros(nz + 1)
+        self.hy_dens_theta_int = np.zeros(nz + 1)
+        self.hy_pressure_int = np.zeros(nz + 1)
+        # stencil weights (fields.py:94-97); kept for API parity, baked into the kernels
+        self.fourth_order_kernel = np.array([-1.0 / 12, 7.0 / 12, 7.0 / 12, -1.0 / 12])
+        self.first_order_kernel = np.array([1.0, -3.0, 3.0, -1.0])
+
+    # -- state arrays ----------------------------------------------------------------------
+    def _get(self, buf):
+        if self._dev_newer[buf]:
+            self._solver.download(buf, out=self._host[buf])
+            self._dev_newer[buf] = False
+        self._host_dirty[buf] = True  # the caller may write through the returned array
+        return self._host[buf]
+
+    def _set(self, buf, value):
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        if value.shape != self.shape:
+            raise ValueError(f"expected shape {self.shape}, got {value.shape}")
+        self._host[buf] = value
+        self._host_dirty[buf] = True
+        self._dev_newer[buf] = False
+
+    state = property(lambda self: self._get(PMW_BUF_STATE), lambda self, v: self._set(PMW_BUF_STATE, v))
+    state_tmp = property(lambda self: self._get(PMW_BUF_TMP), lambda self, v: self._set(PMW_BUF_TMP, v))
+
+    def __getattr__(self, name):
+        # lazily allocated scratch arrays of the reference container
+        if name in _LAZY_SHAPES:
+            lazy = self.__dict__.setdefault("_lazy", {})
+            if name not in lazy:
+                lazy[name] = np.zeros(_LAZY_SHAPES[name](self))
+            return lazy[name]
+        raise AttributeError(name)
+
+    # -- device side (used by the operators in solve/, ics/, post/) ---------------------------
+    def buffer_of(self, array) -> int | None:
+        """Logical buffer id of a host array handed out by this object, else None."""
+        for buf, a in self._host.items():
+            if array is a:
+                return buf
+        return None
+
+    def device(self, params) -> DeviceSolver:
+        """Context for these fields with every host-side change pushed to HBM."""
+        key = (int(params["nx"]), int(params["nz"]), int(params["hs"]), float(params["dx"]),
+               float(params["dz"]), float(params["dt"]))
+        if key[:3] != (self.nx, self.nz, self.hs):
+            raise ValueError("params do not match the grid these fields were allocated for")
+        if self._solver is None or self._solver_key != key:
+            self.sync_host()
+            if self._solver is not None:
+                self._solver.close()
+            self._solver = DeviceSolver(key[0], key[1], key[3], key[4], key[5], hs=key[2])
+            self._solver_key = key
+            self._host_dirty = {PMW_BUF_STATE: True, PMW_BUF_TMP: True}
+        hydro = [getattr(self, n) for n in HYDRO_NAMES]
+        if not self._solver.hydro_matches(hydro):
+            self._solver.set_hydrostatic(*hydro)
+        for buf in (PMW_BUF_STATE, PMW_BUF_TMP):
+            if self._host_dirty[buf]:
+                self._solver.upload(buf, self._host[buf])
+                self._host_dirty[buf] = False
+        return self._solver
+
+    def device_wrote(self, *bufs):
+        for buf in bufs:
+            self._dev_newer[buf] = True
+
+    def sync_host(self, *bufs):
+        """Pull device-side results into the host arrays (without marking them modified)."""
+        for buf in bufs or (PMW_BUF_STATE, PMW_BUF_TMP):
+            if self._dev_newer[buf]:
+                self._solver.download(buf, out=self._host[buf])
+                self._dev_newer[buf] = False
+
+    def close(self):
+        if self._solver is not None:
+            self.sync_host()
+            self._solver.close()
+            self._solver = None
+
+
+def initialize_fields(params) -> Fields:
+    """Allocate the containers for a run (pyminiweather/data/fields.py:58-123)."""
+    return Fields(params["nx"], params["nz"], params["hs"], params["s"])

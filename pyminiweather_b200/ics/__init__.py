@@ -1,0 +1,5 @@
+from .bcs import set_bc_x, set_bc_z
+from .directions import Directions
+from .initial import init
+
+__all__ = ["set_bc_x", "set_bc_z", "Directions", "init"]

@@ -1,0 +1,79 @@
+"""Time integration: ``evolve`` and ``discrete_step`` (mirror of
+pyminiweather/solve/step.py:21-143), running on the fused sm_100a stage kernels.
+
+``evolve`` issues the six RK stages of one step as six kernel launches on rotating device
+buffers (no halo-fill kernels, no interpolation/flux/tendency arrays).  The reference keeps
+the sweep order in a module global (step.py:18); here it lives in the device context, and
+this module exposes the same name as a read/write convenience for the *native* fields of
+the last call.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .._dispatch import check_ic, direction_id, foreign_solver, is_native, writable_f64
+from .._lib import PMW_BUF_STATE, PMW_BUF_TMP
+from ..ics.directions import Directions  # noqa: F401  (re-exported like the reference)
+
+# Strict (foreign-fields) mode: also bring state_tmp back after evolve.  It is scratch in
+# the reference; leaving it on the device halves the PCIe traffic of the drop-in call.
+SYNC_STATE_TMP = False
+
+
+def discrete_step(params, fields, mesh, state_init, state_forcing, state_out, dt, direction) -> None:
+    """One RK stage: halo fill on ``state_forcing`` (in place), interpolation, fluxes,
+    tendencies, ``state_out[interior] = state_init[interior] + dt * tend`` (step.py:63-82).
+    ``state_out`` may alias either input, as in step.py:112-141."""
+    check_ic(params["ic_type"])
+    d = direction_id(direction)
+    shape = (4, params["nz"] + 2 * params["hs"], params["nx"] + 2 * params["hs"])
+    for name, a in (("state_init", state_init), ("state_forcing", state_forcing), ("state_out", state_out)):
+        writable_f64(a, shape, name)
+
+    if is_native(fields):
+        bufs = [fields.buffer_of(a) for a in (state_init, state_forcing, state_out)]
+        if None not in bufs:
+            solver = fields.device(params)
+            solver.discrete_step(d, bufs[0], bufs[1], bufs[2], dt)
+            fields.device_wrote(bufs[1], bufs[2])
+            fields.sync_host(bufs[1], bufs[2])  # explicitly passed arrays are updated on return
+            return
+        solver = fields.device(params)
+        fields.sync_host()
+        fields._host_dirty[PMW_BUF_STATE] = fields._host_dirty[PMW_BUF_TMP] = True
+    else:
+        solver = foreign_solver(fields, params)
+
+    # Generic path for arbitrary host arrays: forcing -> TMP, init -> STATE (or TMP when it is
+    # the same array); BC, then the stage with out aliased to forcing; only the interior of the
+    # result is written to state_out, after forcing has received its new halo cells.
+    solver.upload(PMW_BUF_TMP, state_forcing)
+    init_buf = PMW_BUF_TMP
+    if state_init is not state_forcing:
+        solver.upload(PMW_BUF_STATE, state_init)
+        init_buf = PMW_BUF_STATE
+    (solver.bc_x if d == 1 else solver.bc_z)(PMW_BUF_TMP)
+    solver.download(PMW_BUF_TMP, out=state_forcing)
+    solver.stage(d, init_buf, PMW_BUF_TMP, PMW_BUF_TMP, dt)
+    res = solver.download(PMW_BUF_TMP)
+    hs = params["hs"]
+    state_out[:, hs:-hs, hs:-hs] = res[:, hs:-hs, hs:-hs]
+
+
+def evolve(params, fields, mesh, dt: float = 1e-4) -> None:
+    """Advance by one time step ``dt``: two directional sweeps (Z,X then X,Z, alternating per
+    call) of three RK stages each (step.py:85-143)."""
+    check_ic(params["ic_type"])
+    if is_native(fields):
+        solver = fields.device(params)
+        solver.evolve(1, dt)
+        fields.device_wrote(PMW_BUF_STATE, PMW_BUF_TMP)
+        return
+    solver = foreign_solver(fields, params)
+    shape = (4, params["nz"] + 2 * params["hs"], params["nx"] + 2 * params["hs"])
+    state = writable_f64(fields.state, shape, "fields.state")
+    solver.upload(PMW_BUF_STATE, state)
+    solver.evolve(1, dt)
+    solver.download(PMW_BUF_STATE, out=state)
+    if SYNC_STATE_TMP:
+        solver.download(PMW_BUF_TMP, out=writable_f64(fields.state_tmp, shape, "fields.state_tmp"))

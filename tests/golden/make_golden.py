@@ -1,0 +1,97 @@
+"""Generate the golden fixtures in this directory by running the REAL reference
+(``/root/reference``, NumPy backend) in the build container.
+
+    PYTHONPATH=/root/repo python tests/golden/make_golden.py
+
+Versions used for the committed fixtures are recorded in ``manifest.json``.
+The reference is imported read-only; nothing is copied from it.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "../..")))
+from oracle import reference_runner as rr  # noqa: E402
+
+manifest = {"numpy": np.__version__, "scipy": scipy.__version__,
+            "python": sys.version.split()[0], "files": {}}
+
+
+def hydro(f):
+    return dict(hy_dens_cell=f.hy_dens_cell, hy_dens_theta_cell=f.hy_dens_theta_cell,
+                hy_dens_int=f.hy_dens_int, hy_dens_theta_int=f.hy_dens_theta_int,
+                hy_pressure_int=f.hy_pressure_int)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrs)
+    manifest["files"][name] = sorted(arrs)
+    print("wrote", name, os.path.getsize(path) // 1024, "KiB")
+
+
+def scal(p):
+    return dict(nx=p["nx"], nz=p["nz"], dx=p["dx"], dz=p["dz"], dt=p["dt"])
+
+
+# 1. initial conditions (all five --ic-type choices) on a small grid
+for ic in ["thermal", "collision", "density-current", "gravity", "injection"]:
+    r = rr.ReferenceRun(32, 16, ic)
+    save(f"ic_{ic}_32x16.npz", state=r.fields.state, state_tmp=r.fields.state_tmp,
+         stats=np.array(r.stats()), **hydro(r.fields), **scal(r.params))
+
+# 2. single stages through the reference's discrete_step, all three aliasing patterns
+#    (step.py:112-141), both directions, full arrays including halos
+for ic, (nx, nz) in [("collision", (48, 24)), ("thermal", (37, 19))]:   # second grid is odd-sized
+    r = rr.ReferenceRun(nx, nz, ic)
+    r.evolve(3)                      # non-trivial momentum everywhere
+    f, p = r.fields, r.params
+    out = dict(state0=f.state.copy(), tmp0=f.state_tmp.copy(), **hydro(f), **scal(p))
+    for dname, d in (("x", 1), ("z", 2)):
+        st, tmp = out["state0"].copy(), out["tmp0"].copy()
+        r.discrete_step(st, st, tmp, p["dt"] / 3, d)       # S1: init is forcing
+        out[f"{dname}_s1_state"], out[f"{dname}_s1_tmp"] = st.copy(), tmp.copy()
+        r.discrete_step(st, tmp, tmp, p["dt"] / 2, d)      # S2: out is forcing
+        out[f"{dname}_s2_state"], out[f"{dname}_s2_tmp"] = st.copy(), tmp.copy()
+        r.discrete_step(st, tmp, st, p["dt"] / 1, d)       # S3: out is init
+        out[f"{dname}_s3_state"], out[f"{dname}_s3_tmp"] = st.copy(), tmp.copy()
+    save(f"stages_{ic}_{nx}x{nz}.npz", **out)
+
+# 3. boundary conditions alone on a random array (halos start as garbage)
+r = rr.ReferenceRun(20, 12, "thermal")
+rng = np.random.default_rng(7)
+s = rng.standard_normal(r.fields.state.shape)
+from pyminiweather.ics import set_bc_x, set_bc_z  # noqa: E402  (reference)
+sx, sz = s.copy(), s.copy()
+set_bc_x(r.params, r.fields, sx, "thermal")
+set_bc_z(r.params, r.fields, sz, "thermal")
+save("bc_random_20x12.npz", s=s, after_bc_x=sx, after_bc_z=sz, **hydro(r.fields), **scal(r.params))
+
+# 4. multi-step evolution, BASELINE config 1 grid
+for ic, snaps in [("thermal", [1, 2, 10, 100, 1000]), ("collision", [100]), ("density-current", [100])]:
+    r = rr.ReferenceRun(100, 50, ic)
+    out = dict(state0=r.fields.state.copy(), stats0=np.array(r.stats()), **hydro(r.fields), **scal(r.params))
+    done = 0
+    for n in snaps:
+        r.evolve(n - done)
+        done = n
+        out[f"state_{n}"] = r.fields.state.copy()
+        out[f"tmp_{n}"] = r.fields.state_tmp[:, 2:-2, 2:-2].copy() if n <= 2 else np.zeros(0)
+        out[f"stats_{n}"] = np.array(r.stats())
+    save(f"evolve_{ic}_100x50.npz", **out)
+
+# 5. a mid-size grid, sub-sampled (thermal 512x256, 5 steps)
+r = rr.ReferenceRun(512, 256, "thermal")
+st0 = np.array(r.stats())
+r.evolve(5)
+inner = r.fields.state[:, 2:-2, 2:-2]
+save("evolve_thermal_512x256_5steps_sub8.npz", sub=inner[:, ::8, ::8].copy(),
+     l2=np.array([np.linalg.norm(inner[v]) for v in range(4)]),
+     stats0=st0, stats5=np.array(r.stats()), **scal(r.params))
+
+with open(os.path.join(HERE, "manifest.json"), "w") as fh:
+    json.dump(manifest, fh, indent=1, sort_keys=True)

@@ -1,0 +1,281 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): state <= 1e-11 relative L2 (checked per variable AND on
+the stacked state, interior cells), mass/energy totals <= 1e-12 relative.  Halo-fill kernels are
+copies/exact divisions and are checked bit-exactly.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from helpers import (HYDRO, case_from_golden, interior, make_params, new_case, rel_l2, synthetic_case,
+                     worst_rel_l2)
+from oracle import c_oracle, numpy_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-11
+STATS_TOL = 1e-12
+VARIANTS = [("direct", "libdevice"), ("direct", "background"), ("tma", "libdevice"), ("tma", "background")]
+STATE, TMP, DIR_X, DIR_Z = 0, 1, 1, 2
+
+
+def solver_for(case, variant="tma", pow_mode="background", **tuning):
+    from pyminiweather_b200.engine import DeviceSolver
+    s = DeviceSolver(case.nx, case.nz, case.dx, case.dz, case.dt, variant=variant, pow_mode=pow_mode)
+    s.set_hydrostatic(*[getattr(case, n) for n in HYDRO])
+    if tuning:
+        s.set_tuning(**tuning)
+    s.upload(STATE, case.state)
+    s.upload(TMP, case.state_tmp)
+    return s
+
+
+def assert_stats(got, want):
+    assert abs(got[0] - want[0]) / abs(want[0]) <= STATS_TOL, (got, want)
+    assert abs(got[1] - want[1]) / abs(want[1]) <= STATS_TOL, (got, want)
+
+
+# ---- boundary kernels: bit-exact ---------------------------------------------------------------
+def test_bc_kernels_bit_exact_vs_reference_fixture():
+    g = golden("bc_random_20x12.npz")
+    p, case = case_from_golden(g, "s")
+    s = solver_for(case)
+    s.bc_x(STATE)
+    assert np.array_equal(s.download(STATE), g["after_bc_x"])
+    s.upload(STATE, g["s"])
+    s.bc_z(STATE)
+    assert np.array_equal(s.download(STATE), g["after_bc_z"])
+
+
+# ---- single stages with the reference's three aliasing patterns (step.py:112-141) ---------------
+@pytest.mark.parametrize("variant,pow_mode", VARIANTS)
+@pytest.mark.parametrize("name", ["stages_collision_48x24.npz", "stages_thermal_37x19.npz"])
+def test_discrete_step_vs_reference_fixture(name, variant, pow_mode):
+    g = golden(name)
+    for dname, d in (("x", DIR_X), ("z", DIR_Z)):
+        p, case = case_from_golden(g, "state0", "tmp0")
+        s = solver_for(case, variant, pow_mode)
+        s.discrete_step(d, STATE, STATE, TMP, case.dt / 3)
+        st, tmp = s.download(STATE), s.download(TMP)
+        assert np.array_equal(st, g[f"{dname}_s1_state"])  # forcing: only halo cells change, exactly
+        assert worst_rel_l2(tmp, g[f"{dname}_s1_tmp"]) <= 1e-12
+        s.discrete_step(d, STATE, TMP, TMP, case.dt / 2)   # out aliases forcing
+        s.discrete_step(d, STATE, TMP, STATE, case.dt / 1)  # out aliases init
+        for buf, key in ((STATE, f"{dname}_s3_state"), (TMP, f"{dname}_s3_tmp")):
+            got = s.download(buf)
+            assert worst_rel_l2(got, g[key]) <= 1e-12, (dname, key)
+            mask = np.ones(got.shape, bool)
+            mask[:, 2:-2, 2:-2] = False
+            assert rel_l2(got[mask], g[key][mask]) <= 1e-12, (dname, key, "halo ring")
+        s.close()
+
+
+# ---- multi-step evolution against the reference fixtures (BASELINE config 1) -------------------
+@pytest.mark.parametrize("variant,pow_mode", VARIANTS)
+def test_evolve_thermal_100x50_1000_steps(variant, pow_mode):
+    g = golden("evolve_thermal_100x50.npz")
+    p, case = case_from_golden(g, "state0")
+    s = solver_for(case, variant, pow_mode)
+    assert_stats(s.stats(STATE), g["stats0"])
+    done = 0
+    for n in (1, 2, 10, 100, 1000):
+        s.evolve(n - done)
+        done = n
+        assert worst_rel_l2(s.download(STATE), g[f"state_{n}"]) <= STATE_TOL, n
+        assert_stats(s.stats(STATE), g[f"stats_{n}"])
+        if n <= 2:
+            assert rel_l2(interior(s.download(TMP)), g[f"tmp_{n}"]) <= STATE_TOL
+    s.close()
+
+
+@pytest.mark.parametrize("ic", ["collision", "density-current"])
+def test_evolve_100_steps_other_ics(ic):
+    g = golden(f"evolve_{ic}_100x50.npz")
+    p, case = case_from_golden(g, "state0", ic_type=ic)
+    s = solver_for(case)
+    s.evolve(100)
+    assert worst_rel_l2(s.download(STATE), g["state_100"]) <= STATE_TOL
+    assert_stats(s.stats(STATE), g["stats_100"])
+    s.close()
+
+
+# ---- ragged / odd grids against the NumPy oracle (tile edges, tiny grids) -----------------------
+@pytest.mark.parametrize("variant", ["direct", "tma"])
+@pytest.mark.parametrize("nx,nz", [(4, 4), (5, 7), (37, 19), (130, 70), (257, 33), (160, 16), (318, 65)])
+def test_evolve_odd_grids_vs_oracle(nx, nz, variant):
+    p, case = new_case(nx, nz, "collision")
+    s = solver_for(case, variant)
+    for _ in range(6):
+        no.evolve(case)
+    s.evolve(6)
+    assert worst_rel_l2(s.download(STATE), case.state) <= STATE_TOL
+    assert rel_l2(interior(s.download(TMP)), interior(case.state_tmp)) <= STATE_TOL
+    assert_stats(s.stats(STATE), no.compute_stats(case))
+    s.close()
+
+
+@pytest.mark.parametrize("x_tr,x_p", [(4, 2), (4, 7), (8, 3), (8, 5), (8, 6)])
+def test_all_x_tile_shapes(x_tr, x_p):
+    p, case = new_case(300, 40, "collision")
+    s = solver_for(case, x_tr=x_tr, x_p=x_p)
+    for _ in range(4):
+        no.evolve(case)
+    s.evolve(4)
+    assert worst_rel_l2(s.download(STATE), case.state) <= STATE_TOL
+    s.close()
+
+
+@pytest.mark.parametrize("z_cfg", range(7))
+def test_all_z_tile_shapes(z_cfg):
+    p, case = new_case(200, 75, "collision")
+    s = solver_for(case, z_cfg=z_cfg)
+    for _ in range(4):
+        no.evolve(case)
+    s.evolve(4)
+    assert worst_rel_l2(s.download(STATE), case.state) <= STATE_TOL
+    s.close()
+
+
+def test_pow_fallback_branch_large_perturbation():
+    """|eps| > 1/8 takes the pow() fallback of PMW_POW_BACKGROUND; one stage each way on a state
+    with 25 % rho*theta perturbations must still match the oracle."""
+    p, case = synthetic_case(96, 48)
+    rng = np.random.default_rng(3)
+    case.state[3, 2:-2, 2:-2] = 0.25 * case.hy_dens_theta_cell[2:-2, None] * rng.uniform(-1, 1, (48, 96))
+    case.state_tmp[:] = case.state
+    for d in (DIR_X, DIR_Z):
+        c = case.copy()
+        s = solver_for(c)
+        no.discrete_step(c, c.state, c.state, c.state_tmp, c.dt / 3, d)
+        s.discrete_step(d, STATE, STATE, TMP, c.dt / 3)
+        assert worst_rel_l2(s.download(TMP), c.state_tmp) <= 1e-12
+        s.close()
+
+
+# ---- mid-size grids -----------------------------------------------------------------------------
+def test_thermal_512x256_5_steps_vs_reference_subsample():
+    g = golden("evolve_thermal_512x256_5steps_sub8.npz")
+    p, case = new_case(512, 256, "thermal")
+    s = solver_for(case)
+    assert_stats(s.stats(STATE), g["stats0"])
+    s.evolve(5)
+    got = interior(s.download(STATE))
+    for v in range(4):
+        assert rel_l2(got[v][::8, ::8], g["sub"][v]) <= STATE_TOL
+        assert abs(np.linalg.norm(got[v]) - g["l2"][v]) / g["l2"][v] <= 1e-12
+    assert_stats(s.stats(STATE), g["stats5"])
+    s.close()
+
+
+def test_config2_grid_vs_c_oracle():
+    """BASELINE config 2 (thermal 2048x1024): 4 steps against the multi-threaded C oracle."""
+    p, case = new_case(2048, 1024, "thermal")
+    s = solver_for(case)
+    c = c_oracle.COracle(case)
+    c.evolve(4)
+    s.evolve(4)
+    assert worst_rel_l2(s.download(STATE), case.state) <= STATE_TOL
+    assert_stats(s.stats(STATE), c.stats())
+    s.close()
+
+
+def test_synthetic_config5_slice_vs_c_oracle():
+    """Random-perturbation state (config 5 recipe) on a 4096 x 512 slab, 3 steps."""
+    p, case = synthetic_case(4096, 512)
+    s = solver_for(case)
+    c = c_oracle.COracle(case)
+    c.evolve(3)
+    s.evolve(3)
+    assert worst_rel_l2(s.download(STATE), case.state) <= STATE_TOL
+    assert_stats(s.stats(STATE), c.stats())
+    s.close()
+
+
+# ---- size-independent properties at full size ------------------------------------------------------
+def test_x_translation_invariance_bit_exact():
+    """Periodic in x: shifting the initial state by m columns shifts the result by m columns,
+    bit for bit (every cell sees the same operands whatever tile it lands in)."""
+    p, case = synthetic_case(2048, 256, seed=11)
+    m = 333
+    shifted = case.copy()
+    shifted.state[:, :, 2:-2] = np.roll(case.state[:, :, 2:-2], m, axis=2)
+    shifted.state_tmp[:] = shifted.state
+    a, b = solver_for(case), solver_for(shifted)
+    a.evolve(3)
+    b.evolve(3)
+    ra, rb = interior(a.download(STATE)), interior(b.download(STATE))
+    assert np.array_equal(np.roll(ra, m, axis=2), rb)
+    a.close(); b.close()
+
+
+def test_mass_conservation_and_variant_agreement_full_size():
+    p, case = new_case(2048, 1024, "thermal")
+    a, b = solver_for(case, "tma", "background"), solver_for(case, "direct", "libdevice")
+    m0, e0 = a.stats(STATE)
+    a.evolve(10)
+    b.evolve(10)
+    m1, e1 = a.stats(STATE)
+    assert abs(m1 - m0) / m0 <= 1e-13
+    assert worst_rel_l2(a.download(STATE), b.download(STATE)) <= STATE_TOL
+    assert_stats(a.stats(STATE), b.stats(STATE))
+    a.close(); b.close()
+
+
+def test_mirror_symmetry_of_thermal_bubble():
+    """The thermal bubble is symmetric about x = xlen/2: rho', rho*w, (rho*theta)' stay even and
+    rho*u stays odd under x -> -x (to rounding: the stencil is applied mirrored)."""
+    p, case = new_case(512, 256, "thermal")
+    s = solver_for(case)
+    s.evolve(20)
+    r = interior(s.download(STATE))
+    for v, sign in ((0, 1.0), (1, -1.0), (2, 1.0), (3, 1.0)):
+        assert rel_l2(r[v], sign * r[v][:, ::-1]) <= 1e-9
+    s.close()
+
+
+# ---- diagnostics ------------------------------------------------------------------------------------
+def test_stats_and_solution_variables_vs_oracle():
+    g = golden("evolve_thermal_100x50.npz")
+    p, case = case_from_golden(g, "state_100")
+    s = solver_for(case)
+    assert_stats(s.stats(STATE), g["stats_100"])
+    sv = s.solution_variables(STATE)
+    want = no.compute_solution_variables(case)
+    assert sv.shape == (4, 50, 100)
+    for v in range(4):
+        assert rel_l2(sv[v], want[v]) <= 1e-13
+    s.close()
+
+
+def test_slab_halo_pack_unpack_roundtrip():
+    """Two slabs of one periodic domain exchange edge columns == set_bc_x on the whole domain."""
+    import ctypes
+    from pyminiweather_b200.engine import DeviceSolver
+    p, case = synthetic_case(64, 24, seed=5)
+    whole = case.state.copy()
+    no.set_bc_x(case, whole)
+    import torch
+    slabs = []
+    for r in range(2):
+        s = DeviceSolver(32, 24, case.dx, case.dz, case.dt, periodic_x=False)
+        s.set_hydrostatic(*[getattr(case, n) for n in HYDRO])
+        st = np.zeros((4, 28, 36))
+        st[:, :, 2:-2] = case.state[:, :, 2 + 32 * r: 2 + 32 * (r + 1)]
+        s.upload(STATE, st)
+        slabs.append(s)
+    n = slabs[0].halo_len
+    msg = [[torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(2)] for _ in range(2)]
+    for r in range(2):
+        slabs[r].pack_halo_x(STATE, msg[r][0].data_ptr(), msg[r][1].data_ptr())
+        slabs[r].synchronize()
+    for r in range(2):
+        left, right = (r - 1) % 2, (r + 1) % 2
+        slabs[r].unpack_halo_x(STATE, msg[left][1].data_ptr(), msg[right][0].data_ptr())
+    for r in range(2):
+        got = slabs[r].download(STATE)
+        want = np.zeros_like(got)
+        cols = np.arange(32 * r - 2, 32 * (r + 1) + 2) % 64 + 2
+        want[:, 2:-2, :] = whole[:, 2:-2, :][:, :, cols]
+        assert np.array_equal(got[:, 2:-2, :], want[:, 2:-2, :])
+        slabs[r].close()

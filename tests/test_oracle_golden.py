@@ -1,0 +1,106 @@
+"""The oracles against the committed golden vectors (generated from the real reference by
+tests/golden/make_golden.py).  NumPy oracle: bit-exact.  C oracle: identical up to libm-vs-NumPy
+pow rounding (<= 1e-12 relative L2)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from helpers import HYDRO, case_from_golden, interior, rel_l2, worst_rel_l2
+from oracle import c_oracle, numpy_oracle as no
+
+
+@pytest.mark.parametrize("name", ["stages_collision_48x24.npz", "stages_thermal_37x19.npz"])
+def test_numpy_oracle_single_stages_bit_exact(name):
+    g = golden(name)
+    for dname, d in (("x", no.DIR_X), ("z", no.DIR_Z)):
+        p, case = case_from_golden(g, "state0", "tmp0")
+        st, tmp = case.state, case.state_tmp
+        no.discrete_step(case, st, st, tmp, case.dt / 3, d)
+        assert np.array_equal(st, g[f"{dname}_s1_state"]) and np.array_equal(tmp, g[f"{dname}_s1_tmp"])
+        no.discrete_step(case, st, tmp, tmp, case.dt / 2, d)
+        assert np.array_equal(st, g[f"{dname}_s2_state"]) and np.array_equal(tmp, g[f"{dname}_s2_tmp"])
+        no.discrete_step(case, st, tmp, st, case.dt / 1, d)
+        assert np.array_equal(st, g[f"{dname}_s3_state"]) and np.array_equal(tmp, g[f"{dname}_s3_tmp"])
+
+
+def test_numpy_oracle_bcs_bit_exact():
+    g = golden("bc_random_20x12.npz")
+    p, case = case_from_golden(g, "s")
+    sx, sz = g["s"].copy(), g["s"].copy()
+    no.set_bc_x(case, sx)
+    no.set_bc_z(case, sz)
+    assert np.array_equal(sx, g["after_bc_x"])
+    assert np.array_equal(sz, g["after_bc_z"])
+
+
+@pytest.mark.parametrize("ic,snaps", [("thermal", [1, 2, 10, 100]), ("collision", [100]), ("density-current", [100])])
+def test_numpy_oracle_evolution_bit_exact(ic, snaps):
+    g = golden(f"evolve_{ic}_100x50.npz")
+    p, case = case_from_golden(g, "state0", ic_type=ic)
+    assert no.compute_stats(case) == tuple(g["stats0"])
+    done = 0
+    for n in snaps:
+        for _ in range(n - done):
+            no.evolve(case)
+        done = n
+        assert np.array_equal(case.state, g[f"state_{n}"]), f"{ic} after {n} steps"
+        if n <= 2:
+            assert np.array_equal(interior(case.state_tmp), g[f"tmp_{n}"])
+        assert no.compute_stats(case) == tuple(g[f"stats_{n}"])
+
+
+def test_known_answers_from_baseline_md():
+    """thermal 100x50 mass/energy at start and after 1000 steps."""
+    g = golden("evolve_thermal_100x50.npz")
+    assert g["stats0"][0] == 152576073.38012797 and g["stats0"][1] == 28336407811096.082
+    assert g["stats_1000"][0] == 152576073.38012797 and g["stats_1000"][1] == 28335244607294.58
+    l2 = [np.linalg.norm(interior(g["state_1000"])[v]) for v in range(4)]
+    np.testing.assert_allclose(l2, [0.0886723535534927, 89.98467262041439, 138.7941445224433,
+                                    14.501110483240058], rtol=1e-13)
+
+
+def test_c_oracle_1000_steps_vs_reference():
+    g = golden("evolve_thermal_100x50.npz")
+    p, case = case_from_golden(g, "state0")
+    c = c_oracle.COracle(case)
+    done = 0
+    for n in (1, 2, 10, 100, 1000):
+        c.evolve(n - done)
+        done = n
+        assert worst_rel_l2(case.state, g[f"state_{n}"]) <= 2e-12, n
+        m, e = c.stats()
+        assert abs(m - g[f"stats_{n}"][0]) / m <= 1e-14 and abs(e - g[f"stats_{n}"][1]) / e <= 1e-14
+
+
+@pytest.mark.parametrize("name", ["stages_collision_48x24.npz", "stages_thermal_37x19.npz"])
+def test_c_oracle_single_stages(name):
+    g = golden(name)
+    for dname, d in (("x", no.DIR_X), ("z", no.DIR_Z)):
+        p, case = case_from_golden(g, "state0", "tmp0")
+        c = c_oracle.COracle(case)
+        st, tmp = case.state, case.state_tmp
+        c.discrete_step(st, st, tmp, case.dt / 3, d)
+        c.discrete_step(st, tmp, tmp, case.dt / 2, d)
+        c.discrete_step(st, tmp, st, case.dt / 1, d)
+        assert worst_rel_l2(st, g[f"{dname}_s3_state"]) <= 1e-13
+        assert worst_rel_l2(tmp, g[f"{dname}_s3_tmp"]) <= 1e-13
+        # halo cells are images of interior cells (which carry the pow rounding difference)
+        for a, b in ((st, g[f"{dname}_s3_state"]), (tmp, g[f"{dname}_s3_tmp"])):
+            mask = np.ones(a.shape, bool)
+            mask[:, 2:-2, 2:-2] = False
+            assert rel_l2(a[mask], b[mask]) <= 1e-13
+
+
+def test_mid_size_subsample():
+    """thermal 512x256, 5 steps -- oracle against the sub-sampled fixture."""
+    from helpers import new_case
+    g = golden("evolve_thermal_512x256_5steps_sub8.npz")
+    p, case = new_case(512, 256, "thermal")
+    assert no.compute_stats(case) == tuple(g["stats0"])
+    for _ in range(5):
+        no.evolve(case)
+    assert np.array_equal(interior(case.state)[:, ::8, ::8], g["sub"])
+    assert no.compute_stats(case) == tuple(g["stats5"])
+    np.testing.assert_allclose([np.linalg.norm(interior(case.state)[v]) for v in range(4)],
+                               [0.008059702777914363, 15.331353985886734, 15.377827962984657,
+                                109.44385649207791], rtol=1e-12)
