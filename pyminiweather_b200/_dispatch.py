@@ -20,6 +20,7 @@ from .data.fields import Fields
 from .engine import HYDRO_NAMES, DeviceSolver
 
 _foreign: dict[int, tuple] = {}
+_MAX_FOREIGN = 4  # contexts kept alive for foreign fields objects
 
 UNSUPPORTED_ICS = ("injection", "gravity")
 
@@ -54,11 +55,16 @@ def foreign_solver(fields, params) -> DeviceSolver:
     ent = _foreign.get(id(fields))
     if ent is None or ent[0] != key or ent[2]() is not fields:
         if ent is not None:
-            ent[1].close()
+            _drop(id(fields))
         solver = DeviceSolver(key[0], key[1], key[3], key[4], key[5], hs=key[2])
-        ref = weakref.ref(fields, lambda _r, i=id(fields): _drop(i))
+        try:
+            ref = weakref.ref(fields, lambda _r, i=id(fields): _drop(i))
+        except TypeError:  # object without weakref support: pin it (bounded cache below)
+            ref = (lambda f=fields: f)
         ent = (key, solver, ref)
         _foreign[id(fields)] = ent
+        while len(_foreign) > _MAX_FOREIGN:
+            _drop(next(iter(_foreign)))
     solver = ent[1]
     hydro = [np.ascontiguousarray(getattr(fields, n), dtype=np.float64) for n in HYDRO_NAMES]
     if not solver.hydro_matches(hydro):

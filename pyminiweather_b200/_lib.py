@@ -94,7 +94,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile libpmw.so in-tree for sm_100a (cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH + ".tmp"]
     if verbose:
         cmd += ["-Xptxas", "-v"]

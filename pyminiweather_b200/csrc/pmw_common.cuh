@@ -105,9 +105,12 @@ struct IfaceBg {
 //   DIR_Z = false: compute_flux_x (interpolate.py:105-129)
 //   DIR_Z = true : compute_flux_z (interpolate.py:153-186), `wall` = (k==0 || k==nz)
 // Interpolation weights: fields.py:94-97 (4th-order value, flipped 3rd difference).
-// Differences from the reference's rounding: FMA contraction, one reciprocal of rho instead
+// Differences from the reference's rounding: fused multiply-adds, one reciprocal of rho instead
 // of three divisions, optional polynomial pressure -- all validated at <= 1e-12 rel-L2
-// (tools/arith_probe).
+// (tools/arith_probe).  The library is compiled with -fmad=false and every FMA below is
+// written out: ptxas may otherwise contract mul+add pairs differently in different kernels
+// (PTX mul/add without a rounding modifier are contractible), and then the two kernel
+// variants -- or two tiles of one kernel -- would disagree in the last bit for the same cell.
 template <bool DIR_Z, int POW_MODE>
 __device__ __forceinline__ void interface_flux(const double (&s0)[4], const double (&s1)[4],
                                                const double (&s2)[4], const double (&s3)[4],
@@ -122,7 +125,7 @@ __device__ __forceinline__ void interface_flux(const double (&s0)[4], const doub
         d3[v] = fma(-3.0, s2[v], fma(3.0, s1[v], -s0[v])) + s3[v];
     }
     const double rho = val[DENS] + bg.dens;
-    const double r = 1.0 / rho;
+    const double r = __drcp_rn(rho);
     const double u = val[UMOM] * r;
     double w = val[WMOM] * r;
     const double t = (val[RHOT] + bg.dens_theta) * r;

@@ -80,8 +80,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap)
 // x stage
 //   TR   rows per tile (= warps per CTA)
 //   P    passes of 32 interfaces per row; the tile owns TC = 32P-1 cells per row
-//   box  forcing [4][TR][32P+4]  (array columns c0 .. c0+32P+3; one column of padding keeps
-//        the inner box extent a multiple of 16 bytes), init [4][TR][32P]
+//   box  forcing [4][TR][32P+4], init [4][TR][32P].  TMA needs the box to start on a 16-byte
+//        boundary in global memory, i.e. at an even column; tiles start at multiples of the odd
+//        number 32P-1, so odd tiles load from one column further left (`off` = 1) and index
+//        shared memory one column further right.  The 32P+3 columns a tile can touch fit the
+//        32P+4 wide box (whose extent must be a multiple of 16 bytes anyway).
 // ------------------------------------------------------------------------------------------
 template <int TR, int P>
 struct XTile {
@@ -112,6 +115,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
 
     const int c0 = blockIdx.x * T::TC;  // first interior column of the tile
     const int r0 = blockIdx.y * TR;     // first interior row
+    const int off = c0 & 1;             // box starts at the even column c0 - off
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_forcing);
         if (HAS_INIT) tma_prefetch_desc(&tm_init);
@@ -120,8 +124,8 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&bar, (uint32_t)((T::F_ELEMS + (HAS_INIT ? T::I_ELEMS : 0)) * sizeof(double)));
-        tma_load_3d(sF, &tm_forcing, c0, r0 + HS, 0, &bar);
-        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 + HS, r0 + HS, 0, &bar);
+        tma_load_3d(sF, &tm_forcing, c0 - off, r0 + HS, 0, &bar);
+        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 - off + HS, r0 + HS, 0, &bar);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = r0 + warp;  // interior row of this warp
@@ -129,8 +133,8 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
     const IfaceBg bg = bg_x(a.hy, min(k, a.L.nz - 1) + HS);
     mbar_wait(&bar, 0);
 
-    const double* rowF = sF + warp * T::FW;
-    const double* rowI = sI + warp * T::IW;
+    const double* rowF = sF + warp * T::FW + off;
+    const double* rowI = sI + warp * T::IW + off;
     double carry[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int q = 0; q < P; ++q) {
