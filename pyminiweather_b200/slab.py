@@ -1,0 +1,113 @@
+"""x-slab sharding of the domain across the GPUs of one box (one process per GPU).
+
+The reference has no explicit decomposition: under ``legate --gpus N`` cuPyNumeric partitions
+every array operation implicitly (README.md:7,30,245-249).  Here the grid is split into
+``world`` contiguous slabs of ``nx/world`` columns.  z is not split, so z stages need no
+communication; before every x stage each rank needs its neighbours' two edge columns of the
+forcing state -- ``set_bc_x`` (pyminiweather/ics/bcs.py:35-39) generalised to a periodic ring.
+Diagnostics are all-reduced (2 doubles).
+
+``torch.distributed`` is plumbing only: NCCL ``batch_isend_irecv`` between ring neighbours on
+packed [4][nz][2] messages produced/consumed by ``pack_halo_x_kernel`` / ``unpack_halo_x_kernel``.
+The same class runs on the ``gloo`` backend with a host-side solver stand-in, which is how the
+exchange logic is tested without GPUs (tests/test_slab_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import PMW_BUF_STATE, PMW_BUF_TMP, PMW_DIR_X, PMW_DIR_Z
+
+
+class SlabMesh:
+    """Coordinates of one slab in GLOBAL coordinates, with the MeshData getters ``init`` uses
+    (pyminiweather/mesh.py:25-112)."""
+
+    def __init__(self, params, rank: int, world: int):
+        self.hs = params["hs"]
+        self.dx, self.dz = params["dx"], params["dz"]
+        self.nx_local, self.nz = params["nx"], params["nz"]  # params["nx"] is the slab width
+        self.x0 = rank * self.nx_local * self.dx
+        self._cache = {}
+
+    def get_mesh_int_ext(self):
+        if "ie" not in self._cache:
+            hs, n = self.hs, self.nx_local
+            # same spacing as linspace(-hs*dx, (nx+hs)*dx, nx+2hs, endpoint=False), shifted
+            x = self.x0 + (np.arange(n + 2 * hs) - hs) * self.dx
+            z = np.linspace(-hs * self.dz, (self.nz + hs) * self.dz, self.nz + 2 * hs, endpoint=False)
+            self._cache["ie"] = np.meshgrid(x, z)
+        return self._cache["ie"]
+
+    def get_mesh_vertical_cell_edges(self):
+        return np.linspace(0.0, (self.nz + 1) * self.dz, self.nz + 1, endpoint=False)
+
+    def get_mesh_vertical_cell_centers_int_ext(self):
+        return np.linspace((-self.hs + 0.5) * self.dz, (self.nz + self.hs + 0.5) * self.dz,
+                           self.nz + 2 * self.hs, endpoint=False)
+
+
+class SlabRing:
+    """Drives one slab solver through ``evolve`` with a halo exchange before every x stage.
+
+    ``solver`` needs: evolve_stage, pack_halo_x, unpack_halo_x, stats_device/stats, halo_len and
+    a ``reverse_direction`` property -- i.e. a ``DeviceSolver(periodic_x=False)`` or the NumPy
+    stand-in used by the gloo tests.  ``make_buffer(n)`` returns a 1-D float64 torch tensor on the
+    device the backend communicates from.
+    """
+
+    def __init__(self, solver, rank: int, world: int, make_buffer, dist=None):
+        self.solver, self.rank, self.world = solver, rank, world
+        self.left, self.right = (rank - 1) % world, (rank + 1) % world
+        n = solver.halo_len
+        self.to_left, self.to_right = make_buffer(n), make_buffer(n)
+        self.from_left, self.from_right = make_buffer(n), make_buffer(n)
+        self.stats_buf = make_buffer(2)
+        self.dist = dist
+        self.exchanges = 0
+
+    # -- halo exchange ---------------------------------------------------------------------
+    def exchange_halo_x(self, buf: int):
+        s, dist = self.solver, self.dist
+        s.pack_halo_x(buf, self.to_left.data_ptr(), self.to_right.data_ptr())
+        if self.world == 1:
+            # ring of one: my own edge columns come back as my halos (the reference's set_bc_x)
+            self.from_left.copy_(self.to_right)
+            self.from_right.copy_(self.to_left)
+        else:
+            ops = [dist.P2POp(dist.isend, self.to_left, self.left),
+                   dist.P2POp(dist.isend, self.to_right, self.right),
+                   dist.P2POp(dist.irecv, self.from_left, self.left),
+                   dist.P2POp(dist.irecv, self.from_right, self.right)]
+            if self.world == 2:
+                # both neighbours are the same peer: order the pairs by tag-free FIFO semantics --
+                # rank 0 sends (to_left, to_right), peer receives (from_right, from_left)
+                ops = [dist.P2POp(dist.isend, self.to_left, self.left),
+                       dist.P2POp(dist.irecv, self.from_right, self.right),
+                       dist.P2POp(dist.isend, self.to_right, self.right),
+                       dist.P2POp(dist.irecv, self.from_left, self.left)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        s.unpack_halo_x(buf, self.from_left.data_ptr(), self.from_right.data_ptr())
+        self.exchanges += 1
+
+    # -- time stepping ------------------------------------------------------------------------
+    def evolve(self, nsteps: int = 1, dt: float | None = None):
+        """step.py:85-143 on a slab: same stage sequence as pmw_evolve, plus the exchanges."""
+        s = self.solver
+        for _ in range(nsteps):
+            rev = s.reverse_direction
+            for d in ((PMW_DIR_X, PMW_DIR_Z) if rev else (PMW_DIR_Z, PMW_DIR_X)):
+                for rk in (1, 2, 3):
+                    if d == PMW_DIR_X:
+                        self.exchange_halo_x(PMW_BUF_STATE if rk == 1 else PMW_BUF_TMP)
+                    s.evolve_stage(d, rk, dt)
+            s.reverse_direction = not rev
+
+    def stats(self):
+        """Global (mass, energy): local reduction kernels + all-reduce of 2 doubles."""
+        self.solver.stats_device(PMW_BUF_STATE, self.stats_buf.data_ptr())
+        if self.world > 1:
+            self.dist.all_reduce(self.stats_buf)
+        out = self.stats_buf.cpu().numpy()
+        return float(out[0]), float(out[1])
