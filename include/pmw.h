@@ -142,9 +142,10 @@ int pmw_unpack_halo_x(pmw_ctx *ctx, int buf, const double *dev_from_left,
                       const double *dev_from_right);
 
 /* -- tuning ------------------------------------------------------------------------------
- * Tile shapes of the TMA variant.  Keys: "x_tr" (rows per x tile: 4|8), "x_p" (passes of 32
- * interfaces per x tile row, 2..7; a tile owns 32*x_p-1 cells per row), "z_cfg" (index into
- * the built-in list of z tile shapes {rows, cols, rows-per-thread}). */
+ * Tile shapes of the TMA variant.  Keys: "x_tr" (rows per x tile: 4|8), "x_p" (passes of 64
+ * interfaces per x tile row, 1..3; a tile owns 64*x_p-2 cells per row), "z_cfg" (passes of 4
+ * interface rows per z tile, 1..8; a tile owns 4*z_cfg-1 cell rows x 64 columns), "pdl"
+ * (0|1: programmatic dependent launch between consecutive stage kernels; default 1). */
 int pmw_set_tuning(pmw_ctx *ctx, const char *key, int value);
 int pmw_get_tuning(pmw_ctx *ctx, const char *key, int *value);
 

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pmw.h"
@@ -57,9 +58,8 @@ struct TmapKey {
     CUtensorMap map;
 };
 
-struct ZCfg { int tr, tc, rpt; };
-static const ZCfg kZCfgs[] = {{32, 32, 8}, {16, 64, 8}, {16, 64, 4}, {16, 32, 8}, {32, 64, 16}, {8, 64, 8}, {8, 128, 8}};
-static const int kNumZCfgs = sizeof(kZCfgs) / sizeof(kZCfgs[0]);
+// z tiles: z_cfg = NP, passes of 4 interface rows; a tile owns 4*NP-1 cell rows x 64 columns
+static const int kZPassesMin = 1, kZPassesMax = 8;
 
 struct pmw_ctx {
     pmw_params p;
@@ -76,7 +76,7 @@ struct pmw_ctx {
     cudaStream_t stream;
     int reverse;
     // tuning
-    int x_tr, x_p, z_cfg;
+    int x_tr, x_p, z_cfg, pdl;
     // tensor maps
     EncodeTiledFn encode;
     std::vector<TmapKey> tmaps;
@@ -108,22 +108,9 @@ extern "C" int pmw_version(void) { return 100; }
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// best number of 32-interface passes per x tile: fewest wasted cells, then the widest tile
-static int pick_x_passes(int nx)
-{
-    int best = 4;
-    double best_eff = -1.0;
-    for (int p = 2; p <= 7; ++p) {
-        const int tc = 32 * p - 1;
-        const int tiles = (nx + tc - 1) / tc;
-        const double eff = (double)nx / ((double)tiles * tc);
-        if (eff > best_eff + 1e-9 || (fabs(eff - best_eff) <= 1e-9 && p > best && p <= 5)) {
-            best_eff = eff;
-            best = p;
-        }
-    }
-    return best;
-}
+// number of 64-interface passes per x tile (tile = 64p-2 cells per row): two passes measured best
+// on B200 (tools/sweep_tiles.py); one pass for grids narrower than a two-pass tile
+static int pick_x_passes(int nx) { return nx > 62 ? 2 : 1; }
 
 extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
 {
@@ -170,9 +157,10 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->hydro_set = false;
     c->stream = 0;
     c->reverse = 0;
-    c->x_tr = 8;
+    c->x_tr = 4;
     c->x_p = pick_x_passes(params->nx);
-    c->z_cfg = 1;
+    c->z_cfg = 3;
+    c->pdl = 1;
     c->encode = nullptr;
     c->launches = 0;
     c->timing = false;
@@ -237,11 +225,13 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         NEED(value == 4 || value == 8, "x_tr must be 4 or 8");
         c->x_tr = value;
     } else if (!strcmp(key, "x_p")) {
-        NEED(value >= 2 && value <= 7, "x_p must be in 2..7");
+        NEED(value >= 1 && value <= 3, "x_p must be in 1..3");
         c->x_p = value;
     } else if (!strcmp(key, "z_cfg")) {
-        NEED(value >= 0 && value < kNumZCfgs, "z_cfg must be in 0..%d", kNumZCfgs - 1);
+        NEED(value >= kZPassesMin && value <= kZPassesMax, "z_cfg must be in %d..%d", kZPassesMin, kZPassesMax);
         c->z_cfg = value;
+    } else if (!strcmp(key, "pdl")) {
+        c->pdl = value ? 1 : 0;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -255,6 +245,7 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     if (!strcmp(key, "x_tr")) *value = c->x_tr;
     else if (!strcmp(key, "x_p")) *value = c->x_p;
     else if (!strcmp(key, "z_cfg")) *value = c->z_cfg;
+    else if (!strcmp(key, "pdl")) *value = c->pdl;
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
 }
@@ -410,8 +401,8 @@ static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** ou
             *out = &k.map;
             return PMW_OK;
         }
-    if (c->tmaps.capacity() < 64) c->tmaps.reserve(64);  // keep returned pointers stable
-    NEED(c->tmaps.size() < 64, "tensor-map cache full");
+    if (c->tmaps.capacity() < 256) c->tmaps.reserve(256);  // keep returned pointers stable
+    if (c->tmaps.size() >= 256) c->tmaps.clear();           // tuning sweeps: start over
     TmapKey k;
     k.buf = pbuf; k.bw = bw; k.bh = bh;
     const cuuint64_t gdim[3] = {(cuuint64_t)(c->p.nx + 4), (cuuint64_t)(c->p.nz + 4), (cuuint64_t)NVAR};
@@ -426,6 +417,25 @@ static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** ou
     c->tmaps.push_back(k);
     *out = &c->tmaps.back().map;
     return PMW_OK;
+}
+
+// Launch with the programmatic-stream-serialization attribute when `pdl` is set (the kernel
+// then synchronises with its predecessor through griddepcontrol.wait).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <typename K>
@@ -450,7 +460,8 @@ static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
             if (rc_ != PMW_OK) return rc_;                                           \
             attr_done |= 1ull << c->p.device;                                        \
         }                                                                            \
-        stage_x_tma<TR, P, HI, PM><<<grid, T::THREADS, smem, c->stream>>>(tf, ti, a); \
+        launch_ex(stage_x_tma<TR, P, HI, PM>, grid, dim3(T::THREADS), smem, c->stream, c->pdl && !c->timing, \
+                  tf, ti, a);                                                 \
     } while (0)
     if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
     else          { if (fast) GO(false, 1); else GO(false, 0); }
@@ -458,22 +469,23 @@ static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
     return PMW_OK;
 }
 
-template <int TR, int TC, int RPT>
-static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
+template <int NP>
+static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const StageArgs& a)
 {
-    using T = ZTile<TR, TC, RPT>;
-    const dim3 grid((c->p.nx + TC - 1) / TC, (c->p.nz + TR - 1) / TR);
-    const size_t smem = T::smem_bytes(has_init);
+    using T = ZTile<NP>;
+    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + T::TR - 1) / T::TR);
+    const size_t smem = T::smem_bytes();
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
-#define GO(HI, PM)                                                                         \
-    do {                                                                                   \
-        static unsigned long long attr_done = 0; /* one bit per device */                   \
-        if (!(attr_done >> c->p.device & 1ull)) {                                          \
-            int rc_ = set_smem(stage_z_tma<TR, TC, RPT, HI, PM>, T::smem_bytes(true));     \
-            if (rc_ != PMW_OK) return rc_;                                                 \
-            attr_done |= 1ull << c->p.device;                                              \
-        }                                                                                  \
-        stage_z_tma<TR, TC, RPT, HI, PM><<<grid, T::THREADS, smem, c->stream>>>(tf, ti, a); \
+#define GO(HI, PM)                                                                 \
+    do {                                                                           \
+        static unsigned long long attr_done = 0; /* one bit per device */           \
+        if (!(attr_done >> c->p.device & 1ull)) {                                  \
+            int rc_ = set_smem(stage_z_tma<NP, HI, PM>, T::smem_bytes());          \
+            if (rc_ != PMW_OK) return rc_;                                         \
+            attr_done |= 1ull << c->p.device;                                      \
+        }                                                                          \
+        launch_ex(stage_z_tma<NP, HI, PM>, grid, dim3(T::THREADS), smem, c->stream,  \
+                  c->pdl && !c->timing, tf, a);                                    \
     } while (0)
     if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
     else          { if (fast) GO(false, 1); else GO(false, 0); }
@@ -485,12 +497,9 @@ template <int TR>
 static int dispatch_x_p(pmw_ctx* c, bool hi, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
 {
     switch (c->x_p) {
+        case 1: return launch_x_tma<TR, 1>(c, hi, tf, ti, a);
         case 2: return launch_x_tma<TR, 2>(c, hi, tf, ti, a);
         case 3: return launch_x_tma<TR, 3>(c, hi, tf, ti, a);
-        case 4: return launch_x_tma<TR, 4>(c, hi, tf, ti, a);
-        case 5: return launch_x_tma<TR, 5>(c, hi, tf, ti, a);
-        case 6: return launch_x_tma<TR, 6>(c, hi, tf, ti, a);
-        case 7: return launch_x_tma<TR, 7>(c, hi, tf, ti, a);
     }
     return fail(PMW_EINVAL, "bad x_p %d", c->x_p);
 }
@@ -532,7 +541,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
         CU_TRY(cudaEventRecord(e0, c->stream));
     }
 
-    if (c->p.variant == PMW_VARIANT_DIRECT) {
+    if (c->p.variant == PMW_VARIANT_DIRECT || (c->p.nx & 1)) {  // the TMA kernels pair cells in x
         const dim3 block(64, 4);
         const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4);
         const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
@@ -547,23 +556,23 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
         const CUtensorMap *tf = nullptr, *ti = nullptr;
         int rc;
         if (direction == PMW_DIR_X) {
-            const int fw = 32 * c->x_p + 4, iw = 32 * c->x_p;
+            const int fw = 64 * c->x_p + 4, iw = 64 * c->x_p;
             if ((rc = get_tmap(c, p_forcing, fw, c->x_tr, &tf)) != PMW_OK) return rc;
             if ((rc = get_tmap(c, p_init, iw, c->x_tr, &ti)) != PMW_OK) return rc;
             rc = (c->x_tr == 4) ? dispatch_x_p<4>(c, has_init, *tf, *ti, a) : dispatch_x_p<8>(c, has_init, *tf, *ti, a);
             if (rc != PMW_OK) return rc;
         } else {
-            const ZCfg z = kZCfgs[c->z_cfg];
-            if ((rc = get_tmap(c, p_forcing, z.tc, z.tr + 4, &tf)) != PMW_OK) return rc;
-            if ((rc = get_tmap(c, p_init, z.tc, z.tr, &ti)) != PMW_OK) return rc;
-            switch (c->z_cfg) {
-                case 0: rc = launch_z_tma<32, 32, 8>(c, has_init, *tf, *ti, a); break;
-                case 1: rc = launch_z_tma<16, 64, 8>(c, has_init, *tf, *ti, a); break;
-                case 2: rc = launch_z_tma<16, 64, 4>(c, has_init, *tf, *ti, a); break;
-                case 3: rc = launch_z_tma<16, 32, 8>(c, has_init, *tf, *ti, a); break;
-                case 4: rc = launch_z_tma<32, 64, 16>(c, has_init, *tf, *ti, a); break;
-                case 5: rc = launch_z_tma<8, 64, 8>(c, has_init, *tf, *ti, a); break;
-                case 6: rc = launch_z_tma<8, 128, 8>(c, has_init, *tf, *ti, a); break;
+            const int np = c->z_cfg;
+            if ((rc = get_tmap(c, p_forcing, 64, 4 * np + 3, &tf)) != PMW_OK) return rc;
+            switch (np) {
+                case 1: rc = launch_z_tma<1>(c, has_init, *tf, a); break;
+                case 2: rc = launch_z_tma<2>(c, has_init, *tf, a); break;
+                case 3: rc = launch_z_tma<3>(c, has_init, *tf, a); break;
+                case 4: rc = launch_z_tma<4>(c, has_init, *tf, a); break;
+                case 5: rc = launch_z_tma<5>(c, has_init, *tf, a); break;
+                case 6: rc = launch_z_tma<6>(c, has_init, *tf, a); break;
+                case 7: rc = launch_z_tma<7>(c, has_init, *tf, a); break;
+                case 8: rc = launch_z_tma<8>(c, has_init, *tf, a); break;
                 default: rc = fail(PMW_EINVAL, "bad z_cfg");
             }
             if (rc != PMW_OK) return rc;

@@ -10,17 +10,24 @@
 // Several CTAs are resident per SM, so while one tile computes the TMA loads of the others
 // are in flight: occupancy, not a software pipeline, hides the HBM latency.
 //
-// x stage.  A warp owns one tile row and marches along it in passes of 32 interfaces; lane l
-// of pass q evaluates the flux through interface 32q+l and finalises the cell to the LEFT of
-// it with the neighbour lane's flux (one __shfl_up per variable; the flux of lane 31 is
-// carried into the next pass).  A tile of P passes therefore has 32P interfaces and 32P-1
-// cells: no divergent "extra interface" pass, no block barrier, no flux array.
+// Every thread owns TWO adjacent cells in x: shared-memory reads and global stores are
+// 16-byte (LDS.128 / STG.128), and the two interface-flux evaluations a thread makes per step
+// are independent dependency chains (ILP 2 through the FP64 pipe).
 //
-// z stage.  Lanes run along x (conflict-free shared-memory rows, coalesced stores); a thread
-// marches up RPT rows of one column with a 4-row register window per variable, reusing the
-// previous interface flux, so only 1 in RPT+1 fluxes is recomputed by the thread above.  The
-// solid-wall halo rows (set_bc_z, bcs.py:92-148) are rebuilt in shared memory by the tiles
-// that touch a wall, so z stages never read halo rows from HBM.
+// x stage.  A warp owns one tile row and walks it right to left in passes of 64 interfaces;
+// lane l of pass q evaluates the fluxes through interfaces 64q+2l and 64q+2l+1 and finalises
+// the two cells to the right of them; the third flux it needs comes from lane l+1 by one
+// rotating shuffle per variable (lane 31 receives the flux lane 0 kept from the pass before).
+// No block barrier, no flux array, no divergent "extra interface" pass: a tile of P passes
+// evaluates 64P interfaces for its 64P-2 cells.
+//
+// z stage.  Lanes run along x (conflict-free shared-memory rows, coalesced stores); warps own
+// interface rows; the flux through a cell's top face comes from the warp above through a small
+// shared-memory exchange (one block barrier per pass of 4 rows).  The stage's initial state is
+// read straight from global memory while the fluxes are evaluated (same thread, same cells as
+// its stores: safe for the in-place third stage), which keeps a tile at ~55 KB so that four
+// CTAs are resident per SM.  The solid-wall halo rows (set_bc_z, bcs.py:92-148) are rebuilt
+// in shared memory by the tiles that touch a wall, so z stages never read halo rows from HBM.
 #pragma once
 #include <cuda.h>
 
@@ -71,32 +78,61 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
+// Programmatic dependent launch: stage n+1 is launched while the last wave of stage n drains; its
+// CTAs run their prologue (barrier init, descriptor prefetch, profile loads) and then block here
+// until stage n has completed and flushed its stores.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
+// helpers shared by both stage kernels
+// ------------------------------------------------------------------------------------------
+struct Pair {
+    double a, b;
+};
+__device__ __forceinline__ Pair lds2(const double* p)  // p is 16-byte aligned shared memory
+{
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    return {t.x, t.y};
+}
+
+// Stores the updated cell pair (i, i+1) of interior row k for variable v, plus the periodic /
+// slab-neighbour halo images when the pair is one of the two edge pairs (set_bc_x, bcs.py:35-39,
+// folded into the producer).  `po` points at out[(v=0, k, i)].
+__device__ __forceinline__ void store_pair(const StageArgs& a, double* po, long long voff, bool edge, int i,
+                                           double x, double y)
+{
+    *reinterpret_cast<double2*>(po + voff) = make_double2(x, y);
+    if (edge) {
+        const long long o = (po - a.out) + voff;
+        if (i == 0) *reinterpret_cast<double2*>(a.out_left + o + a.L.nx) = make_double2(x, y);
+        else *reinterpret_cast<double2*>(a.out_right + o - a.L.nx) = make_double2(x, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // x stage
 //   TR   rows per tile (= warps per CTA)
-//   P    passes of 32 interfaces per row; the tile owns TC = 32P-1 cells per row
-//   box  forcing [4][TR][32P+4], init [4][TR][32P].  TMA needs the box to start on a 16-byte
-//        boundary in global memory, i.e. at an even column; tiles start at multiples of the odd
-//        number 32P-1, so odd tiles load from one column further left (`off` = 1) and index
-//        shared memory one column further right.  The 32P+3 columns a tile can touch fit the
-//        32P+4 wide box (whose extent must be a multiple of 16 bytes anyway).
+//   P    passes of 64 interfaces per row; the tile owns TC = 64P-2 cells per row
+//   box  forcing [4][TR][64P+4] starting at array column c0 (even: TMA needs a 16-byte aligned
+//        box origin), init [4][TR][64P] starting at array column c0+2
 // ------------------------------------------------------------------------------------------
 template <int TR, int P>
 struct XTile {
-    static constexpr int TC = 32 * P - 1;
-    static constexpr int FW = 32 * P + 4;
-    static constexpr int IW = 32 * P;
+    static constexpr int TC = 64 * P - 2;
+    static constexpr int FW = 64 * P + 4;
+    static constexpr int IW = 64 * P;
     static constexpr int F_ELEMS = NVAR * TR * FW;
     static constexpr int I_ELEMS = NVAR * TR * IW;
     static constexpr int THREADS = 32 * TR;
     static constexpr size_t smem_bytes(bool has_init)
     {
-        return (size_t)(F_ELEMS + (has_init ? I_ELEMS : 0)) * sizeof(double) + 128;
+        return (size_t)(F_ELEMS + (has_init ? I_ELEMS : 0)) * sizeof(double) + 16;
     }
 };
 
@@ -106,59 +142,71 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
             const StageArgs a)
 {
     using T = XTile<TR, P>;
-    extern __shared__ unsigned char smem_raw[];
-    // TMA destinations need 128-byte alignment
-    double* sF = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    double* sI = sF + T::F_ELEMS;  // F_ELEMS*8 is a multiple of 128 (FW*8*4 = 128*(P+...)): see static_assert
-    static_assert((T::F_ELEMS * 8) % 128 == 0, "init tile must stay 128-byte aligned");
-    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sF = reinterpret_cast<double*>(smem_raw);
+    double* sI = sF + T::F_ELEMS;
+    static_assert((T::F_ELEMS * 8) % 128 == 0 && (T::I_ELEMS * 8) % 128 == 0, "tiles stay 128-byte aligned");
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sI + (HAS_INIT ? T::I_ELEMS : 0));
 
-    const int c0 = blockIdx.x * T::TC;  // first interior column of the tile
+    const int c0 = blockIdx.x * T::TC;  // first interior column of the tile (even)
     const int r0 = blockIdx.y * TR;     // first interior row
-    const int off = c0 & 1;             // box starts at the even column c0 - off
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_forcing);
         if (HAS_INIT) tma_prefetch_desc(&tm_init);
-        mbar_init(&bar, 1);
+        mbar_init(bar, 1);
     }
     __syncthreads();
+    pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bar, (uint32_t)((T::F_ELEMS + (HAS_INIT ? T::I_ELEMS : 0)) * sizeof(double)));
-        tma_load_3d(sF, &tm_forcing, c0 - off, r0 + HS, 0, &bar);
-        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 - off + HS, r0 + HS, 0, &bar);
+        mbar_arrive_expect_tx(bar, (uint32_t)((T::F_ELEMS + (HAS_INIT ? T::I_ELEMS : 0)) * sizeof(double)));
+        tma_load_3d(sF, &tm_forcing, c0, r0 + HS, 0, bar);
+        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 + HS, r0 + HS, 0, bar);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = r0 + warp;  // interior row of this warp
     const bool row_ok = k < a.L.nz;
     const IfaceBg bg = bg_x(a.hy, min(k, a.L.nz - 1) + HS);
-    mbar_wait(&bar, 0);
+    const int nx = a.L.nx;
+    const double* rowF = sF + warp * T::FW + 2 * lane;
+    const double* rowI = sI + warp * T::IW + 2 * lane;
+    double* po = a.out + idx(a.L, 0, min(k, a.L.nz - 1) + HS, c0 + HS + 2 * lane);
+    const int src_lane = (lane + 1) & 31;
+    mbar_wait(bar, 0);
 
-    const double* rowF = sF + warp * T::FW + off;
-    const double* rowI = sI + warp * T::IW + off;
-    double carry[4] = {0.0, 0.0, 0.0, 0.0};
+    double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int li = 32 * q + lane;  // tile-local interface; its taps are tile columns li..li+3
-        double s0[4], s1[4], s2[4], s3[4], flux[4];
+    for (int q = P - 1; q >= 0; --q) {
+        // interfaces li, li+1 (tile-local); taps of interface j are tile columns j..j+3
+        double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const double* p = rowF + v * (TR * T::FW) + li;
-            s0[v] = p[0]; s1[v] = p[1]; s2[v] = p[2]; s3[v] = p[3];
+            const double* p = rowF + v * (TR * T::FW) + 64 * q;
+            const Pair u01 = lds2(p), u23 = lds2(p + 2);
+            t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
         }
-        interface_flux<false, POW_MODE>(s0, s1, s2, s3, bg, a.hv_coeff, false, flux);
-        const int cell = li - 1;   // tile-local cell to the left of interface li
-        const int i = c0 + cell;   // interior column
-        const bool ok = row_ok && cell >= 0 && i < a.L.nx;
+        interface_flux<false, POW_MODE>(t0, t1, t2, t3, bg, a.hv_coeff, false, f0);
+        interface_flux<false, POW_MODE>(t1, t2, t3, t4, bg, a.hv_coeff, false, f1);
+        const int i = c0 + 64 * q + 2 * lane;  // interior column of the left cell of the pair
+        // the rightmost pair of the rightmost pass has no flux to its right: it belongs to the next tile
+        const bool ok = row_ok && i < nx && !(q == P - 1 && lane == 31);
+        const bool edge = a.write_xhalo && (i == 0 || i == nx - 2);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            double fl = __shfl_up_sync(0xffffffffu, flux[v], 1);
-            if (lane == 0) fl = carry[v];
-            carry[v] = __shfl_sync(0xffffffffu, flux[v], 31);
+            const double give = (lane == 0) ? keep[v] : f0[v];
+            const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through interface li+2
+            keep[v] = f0[v];
             if (ok) {
-                // forcing value of cell `cell` is tile column cell+2 = li+1 = tap s1
-                const double ini = HAS_INIT ? rowI[v * (TR * T::IW) + cell] : s1[v];
-                const double tend = (fl - flux[v]) * a.inv_d;
-                store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
+                double ia, ib;  // cell li is tile column li+2
+                if (HAS_INIT) {
+                    const Pair in = lds2(rowI + v * (TR * T::IW) + 64 * q);
+                    ia = in.a; ib = in.b;
+                } else {
+                    ia = t2[v]; ib = t3[v];
+                }
+                const double xa = fma(a.dt_stage, (f0[v] - f1[v]) * a.inv_d, ia);
+                const double xb = fma(a.dt_stage, (f1[v] - fr) * a.inv_d, ib);
+                store_pair(a, po + 64 * q, v * a.L.vstride, edge, i, xa, xb);
             }
         }
     }
@@ -166,59 +214,75 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
 
 // ------------------------------------------------------------------------------------------
 // z stage
-//   tile TR x TC cells; forcing box [4][TR+4][TC] (array rows r0 .. r0+TR+3), init [4][TR][TC]
-//   thread = (column, row group); RPT rows per thread; threads = TC * TR/RPT
+//   tile TR x 64 cells, TR = 4*NP - 1; forcing box [4][TR+4][64] (array rows r0 .. r0+TR+3)
+//   4 warps; the tile's 4*NP interface rows are processed in NP passes of 4 rows, top pass
+//   first; in a pass warp w evaluates interface row 4p+w for its lane's column pair, publishes
+//   the flux pair in shared memory, and after one block barrier finalises the cell row above
+//   that interface with the flux of the row above it (warp w+1 of this pass, or warp 0 of the
+//   pass before).  Flux slots are triple-buffered by pass so that one barrier per pass suffices.
+//   No interface is evaluated twice inside a tile and none of the work is serial per thread:
+//   the dependency chain is one flux long, as in the x stage.
 // ------------------------------------------------------------------------------------------
-template <int TR, int TC, int RPT>
+template <int NP>
 struct ZTile {
-    static_assert(TR % RPT == 0 && TC % 32 == 0, "tile shape");
+    static constexpr int TC = 64;
+    static constexpr int W = 4;                 // warps = interface rows per pass
+    static constexpr int TR = W * NP - 1;       // cell rows owned by the tile
     static constexpr int FH = TR + 4;
     static constexpr int F_ELEMS = NVAR * FH * TC;
-    static constexpr int I_ELEMS = NVAR * TR * TC;
-    static constexpr int THREADS = TC * (TR / RPT);
-    static constexpr size_t smem_bytes(bool has_init)
-    {
-        return (size_t)(F_ELEMS + (has_init ? I_ELEMS : 0)) * sizeof(double) + 128;
-    }
+    static constexpr int X_ELEMS = 3 * NVAR * W * TC;  // flux exchange, 3 pass-buffers
+    static constexpr int H_ELEMS = 4 * W * NP;         // hydrostatic interface profiles of the tile
+    static constexpr int THREADS = 32 * W;
+    static constexpr size_t smem_bytes() { return (size_t)(F_ELEMS + X_ELEMS + H_ELEMS) * sizeof(double) + 16; }
 };
 
-template <int TR, int TC, int RPT, bool HAS_INIT, int POW_MODE>
-__global__ void __launch_bounds__(TC * (TR / RPT))
-stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constant__ CUtensorMap tm_init,
-            const StageArgs a)
+template <int NP, bool HAS_INIT, int POW_MODE>
+__global__ void __launch_bounds__(128)
+stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
 {
-    using T = ZTile<TR, TC, RPT>;
-    extern __shared__ unsigned char smem_raw[];
-    double* sF = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    double* sI = sF + T::F_ELEMS;
-    static_assert((T::F_ELEMS * 8) % 128 == 0, "init tile must stay 128-byte aligned");
-    __shared__ __align__(8) uint64_t bar;
+    using T = ZTile<NP>;
+    constexpr int TC = T::TC, W = T::W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sF = reinterpret_cast<double*>(smem_raw);
+    double* sX = sF + T::F_ELEMS;
+    double* sH = sX + T::X_ELEMS;  // [4][W*NP]: dens, dens_theta, 1/dens_theta, pressure per interface row
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sH + T::H_ELEMS);
 
-    const int nz = a.L.nz;
+    const int nz = a.L.nz, nx = a.L.nx;
     const int c0 = blockIdx.x * TC;
-    const int r0 = blockIdx.y * TR;
+    const int r0 = blockIdx.y * T::TR;
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_forcing);
-        if (HAS_INIT) tma_prefetch_desc(&tm_init);
-        mbar_init(&bar, 1);
+        mbar_init(bar, 1);
+    }
+    if (threadIdx.x < W * NP) {  // the tile's interface profiles (constant data: before the PDL wait)
+        const int kc = min(r0 + (int)threadIdx.x, nz);
+        sH[threadIdx.x] = __ldg(a.hy.dens_int + kc);
+        sH[W * NP + threadIdx.x] = __ldg(a.hy.dens_theta_int + kc);
+        sH[2 * W * NP + threadIdx.x] = __ldg(a.hy.inv_dens_theta_int + kc);
+        sH[3 * W * NP + threadIdx.x] = __ldg(a.hy.pressure_int + kc);
     }
     __syncthreads();
+    pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bar, (uint32_t)((T::F_ELEMS + (HAS_INIT ? T::I_ELEMS : 0)) * sizeof(double)));
-        tma_load_3d(sF, &tm_forcing, c0 + HS, r0, 0, &bar);
-        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 + HS, r0 + HS, 0, &bar);
+        mbar_arrive_expect_tx(bar, (uint32_t)(T::F_ELEMS * sizeof(double)));
+        tma_load_3d(sF, &tm_forcing, c0 + HS, r0, 0, bar);
     }
-    const int col = threadIdx.x % TC;
-    const int grp = threadIdx.x / TC;
-    const int i = c0 + col;
-    mbar_wait(&bar, 0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = 2 * lane;
+    const int i = c0 + col;  // interior column of the left cell of the pair (even)
+    const bool col_ok = i < nx;
+    const bool edge = a.write_xhalo && (i == 0 || i == nx - 2);
+    const long long colbase = idx(a.L, 0, HS, min(i, nx - 2) + HS);  // (v=0, interior row 0, pair)
+    mbar_wait(bar, 0);
 
     // set_bc_z folded in: tiles touching a wall rebuild the two halo rows in shared memory
-    if (a.fuse_bc_z) {
+    {
         const bool bottom = (r0 == 0);
         const int top_lr = nz + HS - r0;  // tile-local row of array row nz+2
         const bool top = top_lr < T::FH;  // (array row nz+1 is then tile-local row top_lr-1 >= 2)
-        if (bottom || top) {
+        if (a.fuse_bc_z && (bottom || top)) {
             for (int e = threadIdx.x; e < NVAR * 2 * TC; e += T::THREADS) {
                 const int c = e % TC, j = (e / TC) & 1, v = e / (2 * TC);
                 if (bottom)
@@ -231,43 +295,62 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
                                    __ldg(a.hy.dens_cell + nz + HS - 1),
                                    __ldg(a.hy.dens_cell + nz + HS + j));
             }
-            __syncthreads();
         }
+        __syncthreads();  // profiles (and rebuilt wall rows) visible to every warp
     }
 
-    const int lr0 = grp * RPT;  // first tile-local cell row of this thread
-    // interface r0+lr0+j (bottom face of cell row lr0+j) uses tile rows lr0+j .. lr0+j+3
-    double w0[4], w1[4], w2[4], w3[4], fprev[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const double* p = sF + (v * T::FH + lr0) * TC + col;
-        w0[v] = p[0]; w1[v] = p[TC]; w2[v] = p[2 * TC];
-        fprev[v] = 0.0;
-    }
+    for (int p = NP - 1; p >= 0; --p) {
+        const int lf = W * p + warp;  // tile-local interface row = tile-local cell row above it
+        const int kf = r0 + lf;       // global interface index; bottom face of interior cell row kf
+        const bool cell_ok = col_ok && kf < nz && !(p == NP - 1 && warp == W - 1);
+        Pair ini[4];
+        if (HAS_INIT && cell_ok) {  // initial state of the cell pair, in flight during the flux evaluation
 #pragma unroll
-    for (int j = 0; j <= RPT; ++j) {
-        const int kf = r0 + lr0 + j;  // global interface index
-        double flux[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) w3[v] = sF[(v * T::FH + lr0 + j + 3) * TC + col];
-        const int kc = min(kf, nz);
-        interface_flux<true, POW_MODE>(w0, w1, w2, w3, bg_z(a.hy, kc), a.hv_coeff, kc == 0 || kc == nz, flux);
-        if (j > 0) {
-            const int k = kf - 1;  // interior cell row below interface kf; its forcing value is tap w1
-            if (k < nz && i < a.L.nx) {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    double tend = (fprev[v] - flux[v]) * a.inv_d;
-                    if (v == WMOM) tend = fma(-w1[DENS], GRAV, tend);
-                    const double ini = HAS_INIT ? sI[(v * TR + lr0 + j - 1) * TC + col] : w1[v];
-                    store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
-                }
+            for (int v = 0; v < 4; ++v) {
+                const double2 t = __ldg(reinterpret_cast<const double2*>(
+                    a.init + colbase + v * a.L.vstride + (long long)kf * a.L.pitch));
+                ini[v] = {t.x, t.y};
             }
         }
+        // taps: tile rows lf .. lf+3; A = left column of the pair, B = right column
+        double a0[4], a1[4], a2[4], a3[4], b0[4], b1[4], b2[4], b3[4], fa[4], fb[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            fprev[v] = flux[v];
-            w0[v] = w1[v]; w1[v] = w2[v]; w2[v] = w3[v];
+            const double* q = sF + (v * T::FH + lf) * TC + col;
+            const Pair r0v = lds2(q), r1v = lds2(q + TC), r2v = lds2(q + 2 * TC), r3v = lds2(q + 3 * TC);
+            a0[v] = r0v.a; b0[v] = r0v.b; a1[v] = r1v.a; b1[v] = r1v.b;
+            a2[v] = r2v.a; b2[v] = r2v.b; a3[v] = r3v.a; b3[v] = r3v.b;
+        }
+        const int kc = min(kf, nz);
+        IfaceBg bg;
+        bg.dens = sH[lf]; bg.dens_theta = sH[W * NP + lf];
+        bg.inv_dens_theta = sH[2 * W * NP + lf]; bg.pressure = sH[3 * W * NP + lf];
+        const bool wall = (kc == 0 || kc == nz);
+        interface_flux<true, POW_MODE>(a0, a1, a2, a3, bg, a.hv_coeff, wall, fa);
+        interface_flux<true, POW_MODE>(b0, b1, b2, b3, bg, a.hv_coeff, wall, fb);
+        double* xw = sX + ((p % 3) * NVAR * W + warp) * TC + col;  // slot [p%3][v][warp][col]
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<double2*>(xw + v * W * TC) = make_double2(fa[v], fb[v]);
+        __syncthreads();
+        if (cell_ok) {
+            // flux through the top face: interface row lf+1
+            const double* xr = (warp < W - 1) ? xw + TC : sX + (((p + 1) % 3) * NVAR * W) * TC + col;
+            double* po = a.out + colbase + (long long)kf * a.L.pitch;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const Pair up = lds2(xr + v * W * TC);
+                double ta = (fa[v] - up.a) * a.inv_d;
+                double tb = (fb[v] - up.b) * a.inv_d;
+                if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250); cell kf is tap 2
+                    ta = fma(-a2[DENS], GRAV, ta);
+                    tb = fma(-b2[DENS], GRAV, tb);
+                }
+                const double ia = HAS_INIT ? ini[v].a : a2[v];
+                const double ib = HAS_INIT ? ini[v].b : b2[v];
+                store_pair(a, po, v * a.L.vstride, edge, i, fma(a.dt_stage, ta, ia), fma(a.dt_stage, tb, ib));
+            }
         }
     }
 }

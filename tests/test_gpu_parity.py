@@ -102,7 +102,7 @@ def test_evolve_100_steps_other_ics(ic):
 
 # ---- ragged / odd grids against the NumPy oracle (tile edges, tiny grids) -----------------------
 @pytest.mark.parametrize("variant", ["direct", "tma"])
-@pytest.mark.parametrize("nx,nz", [(4, 4), (5, 7), (37, 19), (130, 70), (257, 33), (160, 16), (318, 65)])
+@pytest.mark.parametrize("nx,nz", [(4, 4), (5, 7), (6, 5), (37, 19), (62, 9), (126, 70), (130, 70), (257, 33), (160, 16), (318, 65)])
 def test_evolve_odd_grids_vs_oracle(nx, nz, variant):
     p, case = new_case(nx, nz, "collision")
     s = solver_for(case, variant)
@@ -115,7 +115,7 @@ def test_evolve_odd_grids_vs_oracle(nx, nz, variant):
     s.close()
 
 
-@pytest.mark.parametrize("x_tr,x_p", [(4, 2), (4, 7), (8, 3), (8, 5), (8, 6)])
+@pytest.mark.parametrize("x_tr,x_p", [(4, 1), (4, 2), (4, 3), (8, 1), (8, 2), (8, 3)])
 def test_all_x_tile_shapes(x_tr, x_p):
     p, case = new_case(300, 40, "collision")
     s = solver_for(case, x_tr=x_tr, x_p=x_p)
@@ -126,7 +126,7 @@ def test_all_x_tile_shapes(x_tr, x_p):
     s.close()
 
 
-@pytest.mark.parametrize("z_cfg", range(7))
+@pytest.mark.parametrize("z_cfg", range(1, 9))
 def test_all_z_tile_shapes(z_cfg):
     p, case = new_case(200, 75, "collision")
     s = solver_for(case, z_cfg=z_cfg)
