@@ -237,7 +237,8 @@ def run_gpu(args, rank, local_rank, world):
     solver.upload(PMW_BUF_TMP, host_state)
     ring = None
     if world > 1:
-        ring = SlabRing(solver, rank, world, lambda n: torch.zeros(n, dtype=torch.float64, device="cuda"), dist)
+        ring = SlabRing(solver, rank, world, lambda n: torch.zeros(n, dtype=torch.float64, device="cuda"), dist,
+                        args.halo)
 
     def step(n):
         if ring is None:
@@ -363,7 +364,7 @@ def run_gpu(args, rank, local_rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"thermal rising bubble, nx={NX_SLAB * world} nz={NZ} fp64"
                                + (" (BASELINE config 2)" if world == 1 else
-                                  f" = {world} x-slabs of {NX_SLAB}x{NZ}, ring halo exchange per x stage"),
+                                  f" = {world} x-slabs of {NX_SLAB}x{NZ}, ring halo exchange per x stage ({args.halo})"),
                    "nx": NX_SLAB * world, "nz": NZ, "variant": args.variant, "pow_mode": args.pow_mode,
                    "tiles": {k: solver.get_tuning(k) for k in ("x_tr", "x_p", "z_cfg")},
                    "l2": "no flush: working set = 3 state buffers x 67.5 MB = 202 MB per GPU > 126 MB L2 "
@@ -400,6 +401,8 @@ def main():
     ap.add_argument("--variant", default="tma", choices=["tma", "direct"])
     ap.add_argument("--pow-mode", dest="pow_mode", default="background", choices=["background", "libdevice"])
     ap.add_argument("--tune", action="append", help="key=value tile tuning (x_tr, x_p, z_cfg)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="slab halo exchange at N>1: peer-memory stores from the stage kernels, or NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline work")

@@ -141,6 +141,22 @@ int pmw_pack_halo_x(pmw_ctx *ctx, int buf, double *dev_to_left, double *dev_to_r
 int pmw_unpack_halo_x(pmw_ctx *ctx, int buf, const double *dev_from_left,
                       const double *dev_from_right);
 
+/* Peer-memory ring (the production multi-GPU path): instead of pack / send-recv / unpack, the
+ * stage kernels store their edge cell pairs straight into the neighbours' halo columns over
+ * NVLink and publish a per-stage epoch; the neighbours' x stages schedule their edge tiles last
+ * and make them wait for that epoch.  pmw_evolve then works on slab contexts.
+ *   same process : pmw_local_ptrs(other_ctx) -> pmw_connect_peers (peer access must be enabled)
+ *   one process per GPU: pmw_ipc_export -> exchange the 256-byte blobs -> pmw_ipc_open ->
+ *                        pmw_connect_peers.  All ranks must call the stepping functions in the
+ *                        same order; after pmw_upload_state on a connected context a collective
+ *                        barrier is required before stepping.  */
+#define PMW_IPC_BLOB_BYTES 256
+int pmw_ipc_export(pmw_ctx *ctx, void *blob);
+int pmw_ipc_open(pmw_ctx *ctx, const void *blob, void *ptrs_out[4]);
+int pmw_local_ptrs(pmw_ctx *ctx, void *ptrs_out[4]);
+int pmw_connect_peers(pmw_ctx *ctx, void *const left[4], void *const right[4]);
+int pmw_peer_status(pmw_ctx *ctx, int *timed_out);
+
 /* -- tuning ------------------------------------------------------------------------------
  * Tile shapes of the TMA variant.  Keys: "x_tr" (rows per x tile: 4|8), "x_p" (passes of 64
  * interfaces per x tile row, 1..3; a tile owns 64*x_p-2 cells per row), "z_cfg" (passes of 4

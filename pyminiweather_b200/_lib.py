@@ -64,6 +64,11 @@ SIGNATURES = {
     "pmw_halo_len": (C.c_size_t, [_vp]),
     "pmw_pack_halo_x": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "pmw_unpack_halo_x": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "pmw_ipc_export": (C.c_int, [_vp, _vp]),
+    "pmw_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "pmw_local_ptrs": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "pmw_connect_peers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "pmw_peer_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "pmw_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "pmw_get_tuning": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int)]),
     "pmw_buffer_info": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -76,7 +76,7 @@ struct pmw_ctx {
     cudaStream_t stream;
     int reverse;
     // tuning
-    int x_tr, x_p, z_cfg, pdl;
+    int x_tr, x_p, z_cfg, pdl, peer_dbg;
     // tensor maps
     EncodeTiledFn encode;
     std::vector<TmapKey> tmaps;
@@ -84,6 +84,14 @@ struct pmw_ctx {
     double* stats_partial;
     double* stats_out;
     int stats_blocks;
+    // slab ring over peer memory (pmw_connect_peers)
+    bool peers;
+    double* nbr_base[2][3];          // [left|right][physical buffer]: neighbour's base pointers
+    unsigned long long* nbr_flags[2];
+    unsigned long long* flags;       // mine: [0] left neighbour's epoch, [1] right's, [2] watchdog
+    unsigned int* edge_counters;     // last-arriver counter of the push CTAs
+    unsigned long long epoch;        // number of x stages run since pmw_connect_peers
+    std::vector<void*> ipc_opened;
     // bookkeeping
     long long launches;
     bool timing;
@@ -140,6 +148,10 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     for (int b = 0; b < 3; ++b) c->alloc[b] = nullptr;
     c->hydro_blob = nullptr;
     c->stats_partial = c->stats_out = nullptr;
+    c->flags = nullptr;
+    c->edge_counters = nullptr;
+    c->peers = false;
+    c->epoch = 0;
     for (int b = 0; b < 3; ++b) {
         cudaError_t e = cudaMalloc(&c->alloc[b], c->buf_doubles * sizeof(double));
         if (e != cudaSuccess) {
@@ -161,6 +173,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->x_p = pick_x_passes(params->nx);
     c->z_cfg = 3;
     c->pdl = 1;
+    c->peer_dbg = 0;
     c->encode = nullptr;
     c->launches = 0;
     c->timing = false;
@@ -170,7 +183,11 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
         const size_t nhy = (size_t)4 * (params->nz + 4) + (size_t)4 * (params->nz + 1);
         if (cudaMalloc(&c->hydro_blob, nhy * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_partial, (size_t)2 * c->stats_blocks * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess) {
+            cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&c->flags, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(c->flags, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&c->edge_counters, 2 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(c->edge_counters, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
             pmw_destroy(c);
             return fail(PMW_ECUDA, "cudaMalloc of auxiliary buffers failed");
         }
@@ -198,6 +215,9 @@ extern "C" int pmw_destroy(pmw_ctx* c)
     if (c->hydro_blob) cudaFree(c->hydro_blob);
     if (c->stats_partial) cudaFree(c->stats_partial);
     if (c->stats_out) cudaFree(c->stats_out);
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->flags) cudaFree(c->flags);
+    if (c->edge_counters) cudaFree(c->edge_counters);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     delete c;
     return PMW_OK;
@@ -232,6 +252,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         c->z_cfg = value;
     } else if (!strcmp(key, "pdl")) {
         c->pdl = value ? 1 : 0;
+    } else if (!strcmp(key, "peer_dbg")) {
+        c->peer_dbg = value;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -449,7 +471,7 @@ template <int TR, int P>
 static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
 {
     using T = XTile<TR, P>;
-    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + TR - 1) / TR);
+    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + TR - 1) / TR + (a.push_epoch ? 1 : 0));
     const size_t smem = T::smem_bytes(has_init);
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
 #define GO(HI, PM)                                                                   \
@@ -517,12 +539,32 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.out = c->base[p_out];
     a.out_left = a.out;  // single slab: periodic wrap onto itself
     a.out_right = a.out;
+    a.flags = c->flags;
+    a.wait_epoch = 0;
+    a.edge_last = 0;
+    a.push_epoch = 0;
+    a.nbr_forcing_left = a.nbr_forcing_right = nullptr;
+    a.nbr_flags_left = a.nbr_flags_right = nullptr;
+    a.push_counter = c->edge_counters;
+    a.dbg = c->peer_dbg;
     a.hy = c->hy;
     const double d = (direction == PMW_DIR_X) ? c->p.dx : c->p.dz;
     a.hv_coeff = -HV_BETA * d / (16 * c->p.dt);
     a.inv_d = 1.0 / d;
     a.dt_stage = dt_stage;
     a.write_xhalo = (write_xhalo && c->p.periodic_x) ? 1 : 0;
+    if (c->peers && fuse_bc_z && direction == PMW_DIR_X) {
+        // Slab ring, fused path: this x stage first pushes its own edge columns of `forcing` into the
+        // neighbours' halo columns (first row of CTAs) and publishes epoch e; its edge tiles, the last
+        // CTAs of the grid, wait until both neighbours have published e for OUR halo columns.
+        a.push_epoch = a.wait_epoch = ++c->epoch;
+        a.edge_last = 1;
+        a.nbr_forcing_left = c->nbr_base[0][p_forcing];
+        a.nbr_forcing_right = c->nbr_base[1][p_forcing];
+        a.nbr_flags_left = c->nbr_flags[0];
+        a.nbr_flags_right = c->nbr_flags[1];
+    }
+    const int push_rows = a.push_epoch ? 1 : 0;
     a.fuse_bc_z = fuse_bc_z ? 1 : 0;
     const bool has_init = (p_init != p_forcing);
 
@@ -543,7 +585,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
 
     if (c->p.variant == PMW_VARIANT_DIRECT || (c->p.nx & 1)) {  // the TMA kernels pair cells in x
         const dim3 block(64, 4);
-        const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4);
+        const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4 + (direction == PMW_DIR_X ? push_rows : 0));
         const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
         if (direction == PMW_DIR_X) {
             if (fast) stage_x_direct<1><<<grid, block, 0, c->stream>>>(a);
@@ -633,24 +675,31 @@ extern "C" int pmw_evolve_stage(pmw_ctx* c, int direction, int rk_stage, double 
     const int S = c->l2p[PMW_BUF_STATE], T = c->l2p[PMW_BUF_TMP];
     const int p_forcing = (rk_stage == 1) ? S : T;
     if (direction == PMW_DIR_X && !c->xhalo_valid[p_forcing]) {
-        NEED(c->p.periodic_x, "pmw_evolve_stage: x halos of the forcing buffer are stale; a slab context "
-                              "needs pmw_unpack_halo_x (neighbour columns) before every x stage");
-        const int n = NVAR * c->p.nz;
-        bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[p_forcing], c->L);
-        LAUNCHED(c, "bc_x_kernel");
+        if (c->peers) {
+            // nothing to do: in a connected slab every x stage pushes/receives its own halo columns
+        } else {
+            NEED(c->p.periodic_x, "pmw_evolve_stage: x halos of the forcing buffer are stale; a slab context "
+                                  "needs pmw_unpack_halo_x (neighbour columns) before every x stage");
+            const int n = NVAR * c->p.nz;
+            bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[p_forcing], c->L);
+            LAUNCHED(c, "bc_x_kernel");
+        }
         c->xhalo_valid[p_forcing] = true;
     }
+    // Halo images are stored by the stage whose output the next x stage reads: x stages 1 and 2,
+    // and every stage 3 (the next sweep may be an x sweep).  z stages 1 and 2 feed z stages only.
+    const bool images = (direction == PMW_DIR_X) || rk_stage == 3;
     int rc;
     if (rk_stage == 1) {
-        rc = launch_stage(c, direction, S, S, T, dt / 3, true, true);
+        rc = launch_stage(c, direction, S, S, T, dt / 3, images, true);
     } else if (rk_stage == 2) {
-        rc = launch_stage(c, direction, S, T, c->spare, dt / 2, true, true);
+        rc = launch_stage(c, direction, S, T, c->spare, dt / 2, images, true);
         if (rc == PMW_OK) {
             c->l2p[PMW_BUF_TMP] = c->spare;
             c->spare = T;
         }
     } else {
-        rc = launch_stage(c, direction, S, T, S, dt / 1, true, true);
+        rc = launch_stage(c, direction, S, T, S, dt / 1, images, true);
     }
     return rc;
 }
@@ -659,8 +708,9 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
 {
     BIND(c);
     NEED(nsteps >= 0, "pmw_evolve: negative nsteps");
-    NEED(c->p.periodic_x, "pmw_evolve: a slab context (periodic_x=0) must be stepped stage by stage "
-                          "with pmw_evolve_stage and a halo exchange before every x stage");
+    NEED(c->p.periodic_x || c->peers,
+         "pmw_evolve: a slab context (periodic_x=0) needs pmw_connect_peers, or must be stepped stage by "
+         "stage with pmw_evolve_stage and a halo exchange before every x stage");
     for (int n = 0; n < nsteps; ++n) {
         const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
         for (int d = 0; d < 2; ++d)
@@ -790,5 +840,86 @@ extern "C" int pmw_stage_timing_read(pmw_ctx* c, double* mean_ms, long long* cou
     *mean_ms = n ? total / (double)n : 0.0;
     *count = n;
     c->ev_used = 0;
+    return PMW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// slab ring over peer memory (NVLink P2P stores from the stage kernels)
+// ---------------------------------------------------------------------------------------------
+extern "C" int pmw_ipc_export(pmw_ctx* c, void* blob)
+{
+    BIND(c);
+    NEED(blob, "pmw_ipc_export: null blob");
+    cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(blob);
+    for (int b = 0; b < 3; ++b) CU_TRY(cudaIpcGetMemHandle(&h[b], c->alloc[b]));
+    CU_TRY(cudaIpcGetMemHandle(&h[3], c->flags));
+    return PMW_OK;
+}
+
+extern "C" int pmw_ipc_open(pmw_ctx* c, const void* blob, void* ptrs_out[4])
+{
+    BIND(c);
+    NEED(blob && ptrs_out, "pmw_ipc_open: null argument");
+    const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(blob);
+    for (int b = 0; b < 4; ++b) {
+        void* p = nullptr;
+        CU_TRY(cudaIpcOpenMemHandle(&p, h[b], cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened.push_back(p);
+        ptrs_out[b] = p;
+    }
+    return PMW_OK;
+}
+
+extern "C" int pmw_local_ptrs(pmw_ctx* c, void* ptrs_out[4])
+{
+    BIND(c);
+    NEED(ptrs_out, "pmw_local_ptrs: null argument");
+    for (int b = 0; b < 3; ++b) ptrs_out[b] = c->alloc[b];
+    ptrs_out[3] = c->flags;
+    return PMW_OK;
+}
+
+extern "C" int pmw_connect_peers(pmw_ctx* c, void* const left[4], void* const right[4])
+{
+    BIND(c);
+    NEED(!c->p.periodic_x, "pmw_connect_peers: the context was created with periodic_x=1");
+    NEED((c->p.nx & 1) == 0, "pmw_connect_peers: the slab width must be even");
+    NEED(left && right, "pmw_connect_peers: null argument");
+    for (int b = 0; b < 3; ++b) {
+        NEED(left[b] && right[b], "pmw_connect_peers: null buffer pointer");
+        c->nbr_base[0][b] = static_cast<double*>(left[b]) + LPAD;
+        c->nbr_base[1][b] = static_cast<double*>(right[b]) + LPAD;
+    }
+    c->nbr_flags[0] = static_cast<unsigned long long*>(left[3]);
+    c->nbr_flags[1] = static_cast<unsigned long long*>(right[3]);
+    // same-process neighbours on another device: make their memory addressable from this one
+    // (IPC-opened pointers already are)
+    for (int side = 0; side < 2; ++side) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, side ? right[0] : left[0]) == cudaSuccess && at.device != c->p.device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(PMW_ECUDA, "cannot enable peer access %d -> %d: %s", c->p.device, at.device,
+                            cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+    }
+    c->peers = true;
+    c->epoch = 0;
+    CU_TRY(cudaMemsetAsync(c->flags, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < 3; ++b) c->xhalo_valid[b] = false;
+    return PMW_OK;
+}
+
+// 0 = fine; 1 = an edge tile gave up waiting for a neighbour (results are then invalid).
+extern "C" int pmw_peer_status(pmw_ctx* c, int* timed_out)
+{
+    BIND(c);
+    NEED(timed_out, "null pointer");
+    unsigned long long f[4];
+    CU_TRY(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *timed_out = f[2] != 0;
     return PMW_OK;
 }

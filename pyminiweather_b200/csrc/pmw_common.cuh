@@ -67,7 +67,45 @@ struct StageArgs {
     double dt_stage;
     int write_xhalo;  // also store the periodic/neighbour images of the edge columns
     int fuse_bc_z;    // z stages: rebuild the wall halo rows on the fly (set_bc_z folded in)
+    // slab ring over peer memory: an x stage's edge tiles wait until the neighbour that owns the
+    // halo columns has published epoch >= wait_epoch (flags[0]: left neighbour, flags[1]: right,
+    // flags[2]: watchdog error).  wait_epoch == 0: nothing to wait for.
+    unsigned long long* flags;
+    unsigned long long wait_epoch;
+    int edge_last;  // walk tile columns first so that the two edge columns are the last CTAs of the grid
+    // ... while the FIRST row of CTAs of the same kernel (blockIdx.y == 0, present when push_epoch != 0)
+    // stores this slab's own edge columns of `forcing` into the neighbours' halo columns and
+    // publishes push_epoch to them (we are the left neighbour's RIGHT neighbour: its flags[1]).
+    unsigned long long push_epoch;
+    double* nbr_forcing_left;
+    double* nbr_forcing_right;
+    unsigned long long* nbr_flags_left;
+    unsigned long long* nbr_flags_right;
+    unsigned int* push_counter;
+    int dbg;  // development switches (pmw_set_tuning "peer_dbg"); 0 in production
 };
+
+// The push role of an x stage (see StageArgs::push_epoch): every thread of the first row of CTAs.
+__device__ __forceinline__ void push_halo_role(const StageArgs& a)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const Layout& L = a.L;
+    for (int t = blockIdx.x * nthr + tid; t < NVAR * L.nz; t += gridDim.x * nthr) {
+        const int k = t % L.nz, v = t / L.nz;
+        const double2 first = *reinterpret_cast<const double2*>(a.forcing + idx(L, v, k + HS, HS));
+        const double2 last = *reinterpret_cast<const double2*>(a.forcing + idx(L, v, k + HS, L.nx));
+        *reinterpret_cast<double2*>(a.nbr_forcing_left + idx(L, v, k + HS, L.nx + HS)) = first;  // its right halo
+        *reinterpret_cast<double2*>(a.nbr_forcing_right + idx(L, v, k + HS, 0)) = last;          // its left halo
+    }
+    __threadfence_system();  // peer stores (NVLink) ordered before the flag
+    __syncthreads();
+    if (tid == 0 && atomicAdd(a.push_counter, 1u) == gridDim.x - 1) {
+        *a.push_counter = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.nbr_flags_left + 1), "l"(a.push_epoch) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.nbr_flags_right + 0), "l"(a.push_epoch) : "memory");
+    }
+}
 
 // ---------------------------------------------------------------------------------
 // (1+e)^gamma - 1 on |e| <= 1/8: degree-12 polynomial (Chebyshev-node interpolant of

@@ -8,6 +8,23 @@
 
 namespace pmw {
 
+// Bounded spin on a neighbour's epoch flag (see wait_epoch in pmw_tma.cuh; no async-proxy fence
+// needed here, the direct kernels read with ordinary loads -- volatile, not the read-only path,
+// for the halo columns would be wrong; the taps below use ld.global.nc only when not waiting).
+__device__ __forceinline__ void spin_epoch(unsigned long long* flags, int which, unsigned long long epoch)
+{
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + which) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 4000000000LL) {
+            flags[2] = 1ull;
+            break;
+        }
+    } while (true);
+}
+
 // Stores one updated cell and, when asked, its periodic / slab-neighbour halo image
 // (set_bc_x, bcs.py:35-39, folded into the producer of the next x stage's forcing state).
 __device__ __forceinline__ void store_cell(const StageArgs& a, int v, int k, int i, double val)
@@ -40,19 +57,38 @@ __device__ __forceinline__ IfaceBg bg_z(const Hydro& hy, int k /* interface */)
     return bg;
 }
 
+template <int POW_MODE>
+__device__ __forceinline__ void stage_x_direct_cell(const StageArgs& a, int i, int k);
+template <int POW_MODE>
+__device__ __forceinline__ void stage_z_direct_cell(const StageArgs& a, int i, int k);
+
 // x stage: interpolate_x + compute_flux_x + compute_tend_x + update (step.py:69-71,80-82).
 template <int POW_MODE>
 __global__ void __launch_bounds__(256) stage_x_direct(const StageArgs a)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // interior column
-    const int k = blockIdx.y * blockDim.y + threadIdx.y;  // interior row
-    if (i >= a.L.nx || k >= a.L.nz) return;
+    const int push_rows = a.push_epoch ? 1 : 0;  // slab ring: first row of blocks pushes the edge columns
+    if (push_rows && blockIdx.y == 0) {
+        push_halo_role(a);
+        return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                // interior column
+    const int k = (blockIdx.y - push_rows) * blockDim.y + threadIdx.y;  // interior row
+    if (i < a.L.nx && k < a.L.nz) stage_x_direct_cell<POW_MODE>(a, i, k);
+}
+
+template <int POW_MODE>
+__device__ __forceinline__ void stage_x_direct_cell(const StageArgs& a, int i, int k)
+{
+    if (a.wait_epoch) {  // slab ring over peer memory: halo columns come from the neighbours
+        if (i < HS) spin_epoch(a.flags, 0, a.wait_epoch);
+        if (i >= a.L.nx - HS) spin_epoch(a.flags, 1, a.wait_epoch);
+    }
     double s[5][4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         const double* f = a.forcing + idx(a.L, v, k + HS, i);  // array column i = cell i-2
 #pragma unroll
-        for (int j = 0; j < 5; ++j) s[j][v] = __ldg(f + j);
+        for (int j = 0; j < 5; ++j) s[j][v] = a.wait_epoch ? f[j] : __ldg(f + j);
     }
     const IfaceBg bg = bg_x(a.hy, k + HS);
     double fl[4], fr[4];
@@ -72,8 +108,13 @@ __global__ void __launch_bounds__(256) stage_z_direct(const StageArgs a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < a.L.nx && k < a.L.nz) stage_z_direct_cell<POW_MODE>(a, i, k);
+}
+
+template <int POW_MODE>
+__device__ __forceinline__ void stage_z_direct_cell(const StageArgs& a, int i, int k)
+{
     const int nz = a.L.nz;
-    if (i >= a.L.nx || k >= nz) return;
     double s[5][4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {

@@ -84,6 +84,24 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Slab ring: spin until the neighbour's epoch flag (written over NVLink by its signal kernel after
+// the stage that stored our halo columns) reaches `epoch`.  Bounded: on timeout the watchdog word
+// is set and the kernel carries on, so a lost peer can never hang the GPU.
+__device__ __forceinline__ void wait_epoch(unsigned long long* flags, int which, unsigned long long epoch)
+{
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + which) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s
+            flags[2] = 1ull;
+            break;
+        }
+    } while (true);
+    asm volatile("fence.proxy.async;" ::: "memory");  // order the acquire before the TMA (async proxy) reads
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -148,8 +166,30 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
     static_assert((T::F_ELEMS * 8) % 128 == 0 && (T::I_ELEMS * 8) % 128 == 0, "tiles stay 128-byte aligned");
     uint64_t* bar = reinterpret_cast<uint64_t*>(sI + (HAS_INIT ? T::I_ELEMS : 0));
 
-    const int c0 = blockIdx.x * T::TC;  // first interior column of the tile (even)
-    const int r0 = blockIdx.y * TR;     // first interior row
+    // Launch order is blockIdx.x-fastest.  Single slab: tile (blockIdx.x, blockIdx.y), a row of tiles
+    // after the other.  Slab ring (edge_last): the grid is walked column by column, columns in the
+    // order 1, 2, ..., ntx-2, 0, ntx-1, so that the tiles whose halo cells arrive from a neighbour
+    // over NVLink are the last CTAs of the kernel and normally never have to wait.
+    // In a slab ring the kernel has one extra row of CTAs in front (blockIdx.y == 0): they push this
+    // slab's own edge columns to the neighbours instead of computing a tile.
+    const int ntx = gridDim.x;
+    const int push_rows = a.push_epoch ? 1 : 0;
+    const int nty = gridDim.y - push_rows;
+    if (push_rows && blockIdx.y == 0) {
+        pdl_launch_dependents();
+        pdl_wait();
+        push_halo_role(a);
+        return;
+    }
+    int tx = blockIdx.x, ty = blockIdx.y - push_rows;
+    if (a.edge_last) {
+        const int lin = ty * ntx + tx;
+        const int cidx = lin / nty;
+        ty = lin % nty;
+        tx = (cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1);
+    }
+    const int c0 = tx * T::TC;  // first interior column of the tile (even)
+    const int r0 = ty * TR;     // first interior row
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_forcing);
@@ -159,6 +199,10 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
     __syncthreads();
     pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
+        if (a.wait_epoch && !(a.dbg & 2)) {
+            if (tx == 0) wait_epoch(a.flags, 0, a.wait_epoch);
+            if (tx == ntx - 1) wait_epoch(a.flags, 1, a.wait_epoch);
+        }
         mbar_arrive_expect_tx(bar, (uint32_t)((T::F_ELEMS + (HAS_INIT ? T::I_ELEMS : 0)) * sizeof(double)));
         tma_load_3d(sF, &tm_forcing, c0, r0 + HS, 0, bar);
         if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 + HS, r0 + HS, 0, bar);

@@ -166,6 +166,33 @@ class DeviceSolver:
     def unpack_halo_x(self, buf: int, from_left_ptr: int, from_right_ptr: int):
         check(self._lib.pmw_unpack_halo_x(self._h, buf, C.c_void_p(from_left_ptr), C.c_void_p(from_right_ptr)))
 
+    # -- peer-memory ring ----------------------------------------------------------------------------
+    def ipc_export(self) -> bytes:
+        blob = C.create_string_buffer(256)
+        check(self._lib.pmw_ipc_export(self._h, blob))
+        return blob.raw
+
+    def ipc_open(self, blob: bytes):
+        ptrs = (C.c_void_p * 4)()
+        buf = C.create_string_buffer(bytes(blob), 256)
+        check(self._lib.pmw_ipc_open(self._h, buf, ptrs))
+        return [p for p in ptrs]
+
+    def local_ptrs(self):
+        ptrs = (C.c_void_p * 4)()
+        check(self._lib.pmw_local_ptrs(self._h, ptrs))
+        return [p for p in ptrs]
+
+    def connect_peers(self, left_ptrs, right_ptrs):
+        l = (C.c_void_p * 4)(*left_ptrs)
+        r = (C.c_void_p * 4)(*right_ptrs)
+        check(self._lib.pmw_connect_peers(self._h, l, r))
+
+    def peer_timed_out(self) -> bool:
+        t = C.c_int()
+        check(self._lib.pmw_peer_status(self._h, C.byref(t)))
+        return bool(t.value)
+
     # -- tuning / introspection ---------------------------------------------------------------------
     def set_tuning(self, **kv):
         for k, v in kv.items():

@@ -7,10 +7,18 @@ communication; before every x stage each rank needs its neighbours' two edge col
 forcing state -- ``set_bc_x`` (pyminiweather/ics/bcs.py:35-39) generalised to a periodic ring.
 Diagnostics are all-reduced (2 doubles).
 
-``torch.distributed`` is plumbing only: NCCL ``batch_isend_irecv`` between ring neighbours on
-packed [4][nz][2] messages produced/consumed by ``pack_halo_x_kernel`` / ``unpack_halo_x_kernel``.
-The same class runs on the ``gloo`` backend with a host-side solver stand-in, which is how the
-exchange logic is tested without GPUs (tests/test_slab_gloo.py).
+Two exchange paths:
+
+* ``peer`` (production): the stage kernels store their edge cell pairs straight into the
+  neighbours' halo columns through IPC-mapped peer memory (NVLink P2P) and publish a per-stage
+  epoch flag; the neighbours' x stages run their edge tiles last and make them wait for that
+  epoch.  No pack/unpack kernels, no NCCL call, no host involvement per stage: the whole time
+  loop is one ``pmw_evolve`` call per rank.  ``torch.distributed`` only carries the 256-byte IPC
+  handles at start-up, barriers, and the 2-double all-reduce of the diagnostics.
+* ``nccl`` (baseline / fallback): pack kernel -> ``batch_isend_irecv`` between ring neighbours on
+  [4][nz][2] messages -> unpack kernel, before every x stage.  The same code runs on ``gloo`` with
+  a host-side solver stand-in, which is how the exchange logic is tested without GPUs
+  (tests/test_slab_gloo.py).
 """
 from __future__ import annotations
 
@@ -56,15 +64,43 @@ class SlabRing:
     device the backend communicates from.
     """
 
-    def __init__(self, solver, rank: int, world: int, make_buffer, dist=None):
+    def __init__(self, solver, rank: int, world: int, make_buffer, dist=None, mode: str = "nccl"):
         self.solver, self.rank, self.world = solver, rank, world
         self.left, self.right = (rank - 1) % world, (rank + 1) % world
-        n = solver.halo_len
-        self.to_left, self.to_right = make_buffer(n), make_buffer(n)
-        self.from_left, self.from_right = make_buffer(n), make_buffer(n)
         self.stats_buf = make_buffer(2)
         self.dist = dist
         self.exchanges = 0
+        self.mode = mode
+        if mode == "peer":
+            self._connect_peers()
+        elif mode == "nccl":
+            n = solver.halo_len
+            self.to_left, self.to_right = make_buffer(n), make_buffer(n)
+            self.from_left, self.from_right = make_buffer(n), make_buffer(n)
+        else:
+            raise ValueError("mode must be 'peer' or 'nccl'")
+
+    def _connect_peers(self):
+        """Exchange IPC handles of the three state buffers + flag words and map both neighbours."""
+        s, dist = self.solver, self.dist
+        if self.world == 1:
+            mine = s.local_ptrs()
+            s.connect_peers(mine, mine)
+            return
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, s.ipc_export())
+        opened = {}
+        for r in {self.left, self.right}:
+            opened[r] = s.ipc_open(blobs[r])
+        s.connect_peers(opened[self.left], opened[self.right])
+        self.barrier()
+
+    def barrier(self):
+        """Device + process barrier: required after uploads in peer mode (a neighbour may otherwise
+        still be reading the halo columns the next step's first push overwrites)."""
+        self.solver.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
 
     # -- halo exchange ---------------------------------------------------------------------
     def exchange_halo_x(self, buf: int):
@@ -95,6 +131,9 @@ class SlabRing:
     def evolve(self, nsteps: int = 1, dt: float | None = None):
         """step.py:85-143 on a slab: same stage sequence as pmw_evolve, plus the exchanges."""
         s = self.solver
+        if self.mode == "peer":
+            s.evolve(nsteps, dt)  # the exchange lives inside the stage kernels
+            return
         for _ in range(nsteps):
             rev = s.reverse_direction
             for d in ((PMW_DIR_X, PMW_DIR_Z) if rev else (PMW_DIR_Z, PMW_DIR_X)):

@@ -25,7 +25,7 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, nx, nz, nsteps, out_dir):
+def _worker(rank, world, port, nx, nz, nsteps, out_dir, mode):
     import torch
     import torch.distributed as dist
     from pyminiweather_b200.engine import DeviceSolver
@@ -41,26 +41,30 @@ def _worker(rank, world, port, nx, nz, nsteps, out_dir):
         s.set_stream(torch.cuda.current_stream().cuda_stream)
         s.set_hydrostatic(*[getattr(whole, n) for n in HYDRO])
         s.upload(0, st); s.upload(1, st)
-        ring = SlabRing(s, rank, world, lambda n: torch.zeros(n, dtype=torch.float64, device="cuda"), dist)
+        ring = SlabRing(s, rank, world, lambda n: torch.zeros(n, dtype=torch.float64, device="cuda"), dist, mode)
         ring.evolve(nsteps)
         m, e = ring.stats()
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), state=s.download(0), stats=np.array([m, e]))
+        timed_out = s.peer_timed_out() if mode == "peer" else False
+        dist.barrier()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), state=s.download(0), stats=np.array([m, e]),
+                 timed_out=timed_out)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_slab_ring_matches_single_gpu(world, tmp_path):
+def test_slab_ring_matches_single_gpu(world, mode, tmp_path):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from pyminiweather_b200.engine import DeviceSolver
-    nx, nz, nsteps = 256 * world, 96, 4
+    nx, nz, nsteps = 256 * world, 96, 5  # 5 steps: both sweep orders, incl. X-S3 -> X-S1
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, nx, nz, nsteps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, nx, nz, nsteps, str(tmp_path), mode), nprocs=world, join=True)
     _, whole = synthetic_case(nx, nz, seed=9)
     one = DeviceSolver(nx, nz, whole.dx, whole.dz, whole.dt)
     one.set_hydrostatic(*[getattr(whole, n) for n in HYDRO])
@@ -71,6 +75,24 @@ def test_nccl_slab_ring_matches_single_gpu(world, tmp_path):
     nxl = nx // world
     for r in range(world):
         got = np.load(tmp_path / f"rank{r}.npz")
+        assert not bool(got["timed_out"])
         assert np.array_equal(got["state"][:, 2:-2, 2:-2], want[:, 2:-2, 2 + r * nxl: 2 + (r + 1) * nxl])
         assert abs(got["stats"][0] - ws[0]) / ws[0] < 1e-13 and abs(got["stats"][1] - ws[1]) / ws[1] < 1e-13
     one.close()
+
+
+def test_peer_ring_of_one_equals_periodic_single_gpu():
+    """A ring of one slab mapped onto itself through the peer path == the periodic context."""
+    from pyminiweather_b200.engine import DeviceSolver
+    _, whole = synthetic_case(380, 50, seed=2)
+    a = DeviceSolver(380, 50, whole.dx, whole.dz, whole.dt)
+    b = DeviceSolver(380, 50, whole.dx, whole.dz, whole.dt, periodic_x=False)
+    for s in (a, b):
+        s.set_hydrostatic(*[getattr(whole, n) for n in HYDRO])
+        s.upload(0, whole.state); s.upload(1, whole.state)
+    mine = b.local_ptrs()
+    b.connect_peers(mine, mine)
+    a.evolve(5); b.evolve(5)
+    assert not b.peer_timed_out()
+    assert np.array_equal(a.download(0)[:, 2:-2, 2:-2], b.download(0)[:, 2:-2, 2:-2])
+    a.close(); b.close()
