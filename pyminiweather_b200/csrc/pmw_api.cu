@@ -77,6 +77,7 @@ struct pmw_ctx {
     int reverse;
     // tuning
     int x_tr, x_p, z_cfg, pdl, peer_dbg;
+    int l2_hints;  // decimal digits: forcing(S1) init out | forcing(S2,S3): see pmw_set_tuning
     // tensor maps
     EncodeTiledFn encode;
     std::vector<TmapKey> tmaps;
@@ -174,6 +175,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->z_cfg = 3;
     c->pdl = 1;
     c->peer_dbg = 0;
+    c->l2_hints = 1100;  // forcing tiles evict_first, everything else normal (tools/l2_probe.py)
     c->encode = nullptr;
     c->launches = 0;
     c->timing = false;
@@ -254,6 +256,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         c->pdl = value ? 1 : 0;
     } else if (!strcmp(key, "peer_dbg")) {
         c->peer_dbg = value;
+    } else if (!strcmp(key, "l2_hints")) {
+        c->l2_hints = value;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -547,6 +551,13 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.nbr_flags_left = a.nbr_flags_right = nullptr;
     a.push_counter = c->edge_counters;
     a.dbg = c->peer_dbg;
+    {   // l2_hints = decimal "abcd": a = forcing when init==forcing (stage 1), b = forcing otherwise,
+        // c = init, d = out; each 0 normal | 1 evict_first | 2 evict_last
+        const int h = c->l2_hints;
+        a.hint_forcing = (p_init == p_forcing) ? (h / 1000) % 10 : (h / 100) % 10;
+        a.hint_init = (h / 10) % 10;
+        a.hint_out = h % 10;
+    }
     a.hy = c->hy;
     const double d = (direction == PMW_DIR_X) ? c->p.dx : c->p.dz;
     a.hv_coeff = -HV_BETA * d / (16 * c->p.dt);

@@ -83,7 +83,18 @@ struct StageArgs {
     unsigned long long* nbr_flags_right;
     unsigned int* push_counter;
     int dbg;  // development switches (pmw_set_tuning "peer_dbg"); 0 in production
+    // L2 eviction priority per operand: 0 normal, 1 evict_first, 2 evict_last (createpolicy)
+    int hint_forcing, hint_init, hint_out;
 };
+
+__device__ __forceinline__ unsigned long long l2_policy(int kind)
+{
+    unsigned long long p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 
 // The push role of an x stage (see StageArgs::push_epoch): every thread of the first row of CTAs.
 __device__ __forceinline__ void push_halo_role(const StageArgs& a)

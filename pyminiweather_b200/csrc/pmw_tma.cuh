@@ -70,12 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 // 3-D tiled TMA load global -> shared, completing `bar` with the box byte count.
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y, int z,
-                                            uint64_t* bar)
+                                            uint64_t* bar, unsigned long long policy)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 // Programmatic dependent launch: stage n+1 is launched while the last wave of stage n drains; its
@@ -123,9 +123,10 @@ __device__ __forceinline__ Pair lds2(const double* p)  // p is 16-byte aligned s
 // slab-neighbour halo images when the pair is one of the two edge pairs (set_bc_x, bcs.py:35-39,
 // folded into the producer).  `po` points at out[(v=0, k, i)].
 __device__ __forceinline__ void store_pair(const StageArgs& a, double* po, long long voff, bool edge, int i,
-                                           double x, double y)
+                                           double x, double y, unsigned long long policy)
 {
-    *reinterpret_cast<double2*>(po + voff) = make_double2(x, y);
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(po + voff), "d"(x), "d"(y), "l"(policy)
+                 : "memory");
     if (edge) {
         const long long o = (po - a.out) + voff;
         if (i == 0) *reinterpret_cast<double2*>(a.out_left + o + a.L.nx) = make_double2(x, y);
@@ -204,8 +205,8 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
             if (tx == ntx - 1) wait_epoch(a.flags, 1, a.wait_epoch);
         }
         mbar_arrive_expect_tx(bar, (uint32_t)((T::F_ELEMS + (HAS_INIT ? T::I_ELEMS : 0)) * sizeof(double)));
-        tma_load_3d(sF, &tm_forcing, c0, r0 + HS, 0, bar);
-        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 + HS, r0 + HS, 0, bar);
+        tma_load_3d(sF, &tm_forcing, c0, r0 + HS, 0, bar, l2_policy(a.hint_forcing));
+        if (HAS_INIT) tma_load_3d(sI, &tm_init, c0 + HS, r0 + HS, 0, bar, l2_policy(a.hint_init));
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = r0 + warp;  // interior row of this warp
@@ -216,6 +217,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
     const double* rowI = sI + warp * T::IW + 2 * lane;
     double* po = a.out + idx(a.L, 0, min(k, a.L.nz - 1) + HS, c0 + HS + 2 * lane);
     const int src_lane = (lane + 1) & 31;
+    const unsigned long long pol_out = l2_policy(a.hint_out);
     mbar_wait(bar, 0);
 
     double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
@@ -250,7 +252,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
                 }
                 const double xa = fma(a.dt_stage, (f0[v] - f1[v]) * a.inv_d, ia);
                 const double xb = fma(a.dt_stage, (f1[v] - fr) * a.inv_d, ib);
-                store_pair(a, po + 64 * q, v * a.L.vstride, edge, i, xa, xb);
+                store_pair(a, po + 64 * q, v * a.L.vstride, edge, i, xa, xb, pol_out);
             }
         }
     }
@@ -263,7 +265,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
 //   first; in a pass warp w evaluates interface row 4p+w for its lane's column pair, publishes
 //   the flux pair in shared memory, and after one block barrier finalises the cell row above
 //   that interface with the flux of the row above it (warp w+1 of this pass, or warp 0 of the
-//   pass before).  Flux slots are triple-buffered by pass so that one barrier per pass suffices.
+//   pass before).  Every pass has its own flux slot (dead tile rows), so one barrier per pass suffices.
 //   No interface is evaluated twice inside a tile and none of the work is serial per thread:
 //   the dependency chain is one flux long, as in the x stage.
 // ------------------------------------------------------------------------------------------
@@ -274,14 +276,15 @@ struct ZTile {
     static constexpr int TR = W * NP - 1;       // cell rows owned by the tile
     static constexpr int FH = TR + 4;
     static constexpr int F_ELEMS = NVAR * FH * TC;
-    static constexpr int X_ELEMS = 3 * NVAR * W * TC;  // flux exchange, 3 pass-buffers
+    static constexpr int X_ELEMS = NVAR * W * TC;      // flux exchange slot of the top pass (the other
+                                                       // passes reuse tile rows that are already dead)
     static constexpr int H_ELEMS = 4 * W * NP;         // hydrostatic interface profiles of the tile
     static constexpr int THREADS = 32 * W;
     static constexpr size_t smem_bytes() { return (size_t)(F_ELEMS + X_ELEMS + H_ELEMS) * sizeof(double) + 16; }
 };
 
 template <int NP, bool HAS_INIT, int POW_MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, HAS_INIT ? 4 : 5)  // 5 CTAs/SM would spill the init registers
 stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
 {
     using T = ZTile<NP>;
@@ -311,7 +314,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
     pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar, (uint32_t)(T::F_ELEMS * sizeof(double)));
-        tma_load_3d(sF, &tm_forcing, c0 + HS, r0, 0, bar);
+        tma_load_3d(sF, &tm_forcing, c0 + HS, r0, 0, bar, l2_policy(a.hint_forcing));
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = 2 * lane;
@@ -319,6 +322,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
     const bool col_ok = i < nx;
     const bool edge = a.write_xhalo && (i == 0 || i == nx - 2);
     const long long colbase = idx(a.L, 0, HS, min(i, nx - 2) + HS);  // (v=0, interior row 0, pair)
+    const unsigned long long pol_out = l2_policy(a.hint_out), pol_init = l2_policy(a.hint_init);
     mbar_wait(bar, 0);
 
     // set_bc_z folded in: tiles touching a wall rebuild the two halo rows in shared memory
@@ -352,9 +356,9 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
         if (HAS_INIT && cell_ok) {  // initial state of the cell pair, in flight during the flux evaluation
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const double2 t = __ldg(reinterpret_cast<const double2*>(
-                    a.init + colbase + v * a.L.vstride + (long long)kf * a.L.pitch));
-                ini[v] = {t.x, t.y};
+                const double* src = a.init + colbase + v * a.L.vstride + (long long)kf * a.L.pitch;
+                asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                             : "=d"(ini[v].a), "=d"(ini[v].b) : "l"(src), "l"(pol_init));
             }
         }
         // taps: tile rows lf .. lf+3; A = left column of the pair, B = right column
@@ -373,18 +377,29 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
         const bool wall = (kc == 0 || kc == nz);
         interface_flux<true, POW_MODE>(a0, a1, a2, a3, bg, a.hv_coeff, wall, fa);
         interface_flux<true, POW_MODE>(b0, b1, b2, b3, bg, a.hv_coeff, wall, fb);
-        double* xw = sX + ((p % 3) * NVAR * W + warp) * TC + col;  // slot [p%3][v][warp][col]
+        // Flux exchange slot of pass p: [v][warp][col].  The top pass has its own small buffer; pass
+        // p < NP-1 uses tile rows 4p+7 .. 4p+10 of each variable plane, which only pass p+1 read and
+        // which are dead once every warp is past that pass's barrier.  Slots of different passes
+        // never overlap, so one barrier per pass is enough.
+        double* const xbase = (p == NP - 1) ? sX : sF + (W * p + 7) * TC;
+        constexpr int xstride_top = W * TC, xstride_f = T::FH * TC;
+        const int xstride = (p == NP - 1) ? xstride_top : xstride_f;
+        double* xw = xbase + warp * TC + col;
 #pragma unroll
         for (int v = 0; v < 4; ++v)
-            *reinterpret_cast<double2*>(xw + v * W * TC) = make_double2(fa[v], fb[v]);
+            *reinterpret_cast<double2*>(xw + v * xstride) = make_double2(fa[v], fb[v]);
         __syncthreads();
         if (cell_ok) {
-            // flux through the top face: interface row lf+1
-            const double* xr = (warp < W - 1) ? xw + TC : sX + (((p + 1) % 3) * NVAR * W) * TC + col;
+            // flux through the top face: interface row lf+1 = warp w+1 of this pass, or warp 0 of the
+            // pass above (p+1)
+            const double* const ubase = (p + 1 == NP - 1) ? sX : sF + (W * (p + 1) + 7) * TC;
+            const int ustride = (p + 1 == NP - 1) ? xstride_top : xstride_f;
+            const double* xr = (warp < W - 1) ? xw + TC : ubase + col;
+            const int rstride = (warp < W - 1) ? xstride : ustride;
             double* po = a.out + colbase + (long long)kf * a.L.pitch;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const Pair up = lds2(xr + v * W * TC);
+                const Pair up = lds2(xr + v * rstride);
                 double ta = (fa[v] - up.a) * a.inv_d;
                 double tb = (fb[v] - up.b) * a.inv_d;
                 if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250); cell kf is tap 2
@@ -393,7 +408,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
                 }
                 const double ia = HAS_INIT ? ini[v].a : a2[v];
                 const double ib = HAS_INIT ? ini[v].b : b2[v];
-                store_pair(a, po, v * a.L.vstride, edge, i, fma(a.dt_stage, ta, ia), fma(a.dt_stage, tb, ib));
+                store_pair(a, po, v * a.L.vstride, edge, i, fma(a.dt_stage, ta, ia), fma(a.dt_stage, tb, ib), pol_out);
             }
         }
     }
