@@ -132,6 +132,17 @@ int pmw_stats_device(pmw_ctx *ctx, int buf, double *dev_out2);
 /* compute_solution_variables (pyminiweather/post/stats.py:38-69): host [4][nz][nx]. */
 int pmw_solution_variables(pmw_ctx *ctx, int buf, double *host_out);
 
+/* Unfused operators, for code written against the reference's individual functions (not the hot
+ * path; the fused stage kernels never materialise these arrays).  Dense host arrays in the
+ * reference's shapes (pyminiweather/data/fields.py:70-78):
+ *   interpolate_x/z   (solve/interpolate.py:10-79):   vals, d3 = [4][nz][nx+1] (x) / [4][nz+1][nx] (z)
+ *   compute_flux_x/z  (solve/interpolate.py:82-186):  flux [4][nz+1][nx+1], sub-block updated
+ *   compute_tend_x/z  (solve/interpolate.py:189-250): tend [4][nz][nx]; z reads rho' of `state_buf` */
+int pmw_interpolate(pmw_ctx *ctx, int direction, int buf, double *host_vals, double *host_d3);
+int pmw_compute_flux(pmw_ctx *ctx, int direction, const double *host_vals, const double *host_d3,
+                     double *host_flux);
+int pmw_compute_tend(pmw_ctx *ctx, int direction, const double *host_flux, int state_buf, double *host_tend);
+
 /* -- x-slab sharding (one context per GPU) ---------------------------------------- */
 /* Edge columns of `buf` as two contiguous device messages of pmw_halo_len() doubles each
  * ([4][nz][2]): to_left = my first two interior columns, to_right = my last two.  This is

@@ -67,7 +67,7 @@ def foreign_solver(fields, params) -> DeviceSolver:
             _drop(next(iter(_foreign)))
     solver = ent[1]
     hydro = [np.ascontiguousarray(getattr(fields, n), dtype=np.float64) for n in HYDRO_NAMES]
-    if not solver.hydro_matches(hydro):
+    if all(np.all(h > 0) for h in hydro[:4]) and not solver.hydro_matches(hydro):
         solver.set_hydrostatic(*hydro)
     return solver
 

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libpmw.so")
 SOURCES = ["pmw_api.cu"]
-HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_aux.cuh"]
+HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_aux.cuh", "pmw_unfused.cuh"]
 
 PMW_BUF_STATE, PMW_BUF_TMP = 0, 1
 PMW_DIR_X, PMW_DIR_Z = 1, 2
@@ -61,6 +61,9 @@ SIGNATURES = {
     "pmw_stats": (C.c_int, [_vp, C.c_int, _dp]),
     "pmw_stats_device": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_solution_variables": (C.c_int, [_vp, C.c_int, _vp]),
+    "pmw_interpolate": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "pmw_compute_flux": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "pmw_compute_tend": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "pmw_halo_len": (C.c_size_t, [_vp]),
     "pmw_pack_halo_x": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "pmw_unpack_halo_x": (C.c_int, [_vp, C.c_int, _vp, _vp]),

@@ -15,6 +15,7 @@
 #include "pmw_aux.cuh"
 #include "pmw_direct.cuh"
 #include "pmw_tma.cuh"
+#include "pmw_unfused.cuh"
 
 using namespace pmw;
 
@@ -932,5 +933,84 @@ extern "C" int pmw_peer_status(pmw_ctx* c, int* timed_out)
     CU_TRY(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     *timed_out = f[2] != 0;
+    return PMW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// unfused operator shims (API parity with the reference's individual operators; not the hot path)
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    double* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(double)); }
+};
+
+extern "C" int pmw_interpolate(pmw_ctx* c, int direction, int buf, double* host_vals, double* host_d3)
+{
+    BIND(c);
+    CHECK_BUF(buf);
+    NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_interpolate: bad direction %d", direction);
+    NEED(host_vals && host_d3, "pmw_interpolate: null output");
+    const bool z = direction == PMW_DIR_Z;
+    const size_t n = (size_t)NVAR * (z ? c->p.nz + 1 : c->p.nz) * (z ? c->p.nx : c->p.nx + 1);
+    DevBuf vals, d3;
+    CU_TRY(vals.alloc(n));
+    CU_TRY(d3.alloc(n));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (z) interpolate_kernel<true><<<blocks, 256, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, vals.p, d3.p);
+    else interpolate_kernel<false><<<blocks, 256, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, vals.p, d3.p);
+    LAUNCHED(c, "interpolate_kernel");
+    CU_TRY(cudaMemcpyAsync(host_vals, vals.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(host_d3, d3.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return PMW_OK;
+}
+
+extern "C" int pmw_compute_flux(pmw_ctx* c, int direction, const double* host_vals, const double* host_d3,
+                                double* host_flux)
+{
+    BIND(c);
+    NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_compute_flux: bad direction %d", direction);
+    NEED(host_vals && host_d3 && host_flux, "pmw_compute_flux: null argument");
+    NEED(c->hydro_set, "pmw_compute_flux: hydrostatic profiles not set");
+    const bool z = direction == PMW_DIR_Z;
+    const size_t plane = (size_t)(z ? c->p.nz + 1 : c->p.nz) * (z ? c->p.nx : c->p.nx + 1);
+    const size_t nf = (size_t)NVAR * (c->p.nz + 1) * (c->p.nx + 1);
+    DevBuf vals, d3, flux;
+    CU_TRY(vals.alloc(NVAR * plane));
+    CU_TRY(d3.alloc(NVAR * plane));
+    CU_TRY(flux.alloc(nf));
+    CU_TRY(cudaMemcpyAsync(vals.p, host_vals, NVAR * plane * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(d3.p, host_d3, NVAR * plane * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(flux.p, host_flux, nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const double d = z ? c->p.dz : c->p.dx;
+    const double hv = -HV_BETA * d / (16 * c->p.dt);
+    const unsigned blocks = (unsigned)((plane + 255) / 256);
+    if (z) flux_kernel<true><<<blocks, 256, 0, c->stream>>>(vals.p, d3.p, c->L, c->hy, hv, flux.p);
+    else flux_kernel<false><<<blocks, 256, 0, c->stream>>>(vals.p, d3.p, c->L, c->hy, hv, flux.p);
+    LAUNCHED(c, "flux_kernel");
+    CU_TRY(cudaMemcpyAsync(host_flux, flux.p, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return PMW_OK;
+}
+
+extern "C" int pmw_compute_tend(pmw_ctx* c, int direction, const double* host_flux, int state_buf, double* host_tend)
+{
+    BIND(c);
+    CHECK_BUF(state_buf);
+    NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_compute_tend: bad direction %d", direction);
+    NEED(host_flux && host_tend, "pmw_compute_tend: null argument");
+    const bool z = direction == PMW_DIR_Z;
+    const size_t nf = (size_t)NVAR * (c->p.nz + 1) * (c->p.nx + 1), nt = (size_t)NVAR * c->p.nz * c->p.nx;
+    DevBuf flux, tend;
+    CU_TRY(flux.alloc(nf));
+    CU_TRY(tend.alloc(nt));
+    CU_TRY(cudaMemcpyAsync(flux.p, host_flux, nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const unsigned blocks = (unsigned)((nt + 255) / 256);
+    if (z) tend_kernel<true><<<blocks, 256, 0, c->stream>>>(flux.p, c->base[c->l2p[state_buf]], c->L, c->p.dz, tend.p);
+    else tend_kernel<false><<<blocks, 256, 0, c->stream>>>(flux.p, c->base[c->l2p[state_buf]], c->L, c->p.dx, tend.p);
+    LAUNCHED(c, "tend_kernel");
+    CU_TRY(cudaMemcpyAsync(host_tend, tend.p, nt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
     return PMW_OK;
 }

@@ -100,7 +100,9 @@ class Fields:
             self._solver_key = key
             self._host_dirty = {PMW_BUF_STATE: True, PMW_BUF_TMP: True}
         hydro = [getattr(self, n) for n in HYDRO_NAMES]
-        if not self._solver.hydro_matches(hydro):
+        # profiles still all-zero (init() not run yet): leave them unset -- operators that need them
+        # then fail with "hydrostatic profiles not set", the pure stencil shims work regardless
+        if all(np.all(h > 0) for h in hydro[:4]) and not self._solver.hydro_matches(hydro):
             self._solver.set_hydrostatic(*hydro)
         for buf in (PMW_BUF_STATE, PMW_BUF_TMP):
             if self._host_dirty[buf]:

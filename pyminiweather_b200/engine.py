@@ -155,6 +155,19 @@ class DeviceSolver:
         check(self._lib.pmw_solution_variables(self._h, buf, C.c_void_p(out.ctypes.data)))
         return out
 
+    # -- unfused operator shims ---------------------------------------------------------------------
+    def interpolate(self, direction: int, buf: int, vals: np.ndarray, d3: np.ndarray):
+        check(self._lib.pmw_interpolate(self._h, direction, buf, C.c_void_p(vals.ctypes.data),
+                                        C.c_void_p(d3.ctypes.data)))
+
+    def compute_flux(self, direction: int, vals: np.ndarray, d3: np.ndarray, flux: np.ndarray):
+        check(self._lib.pmw_compute_flux(self._h, direction, C.c_void_p(vals.ctypes.data),
+                                         C.c_void_p(d3.ctypes.data), C.c_void_p(flux.ctypes.data)))
+
+    def compute_tend(self, direction: int, flux: np.ndarray, state_buf: int, tend: np.ndarray):
+        check(self._lib.pmw_compute_tend(self._h, direction, C.c_void_p(flux.ctypes.data), state_buf,
+                                         C.c_void_p(tend.ctypes.data)))
+
     # -- slab halo messages ----------------------------------------------------------------------
     @property
     def halo_len(self) -> int:

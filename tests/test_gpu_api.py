@@ -148,3 +148,101 @@ def test_unsupported_configurations_raise():
     with pytest.raises(ValueError):
         s.upload(0, np.zeros((4, 20, 35)))
     s.close()
+
+
+# ---- unfused operator shims (reference: pyminiweather/solve/interpolate.py) ------------------------
+def test_reference_test_interpolate_on_the_gpu_shims():
+    """tests/unit/test_interpolate.py:11-63 of the reference, against our interpolate_x/z: arange
+    state at the default 200x100 grid vs scipy.signal.convolve2d, np.allclose."""
+    from scipy.signal import convolve2d
+    from pyminiweather_b200.data import initialize_fields
+    from pyminiweather_b200.solve import interpolate_x, interpolate_z
+    p = make_params(200, 100)
+    nx, nz = 200, 100
+    f = initialize_fields(p)
+    state = np.arange(np.prod(f.shape)).astype(np.float64).reshape(f.shape)
+    f.state = state
+    k4 = np.array([-1.0 / 12, 7.0 / 12, 7.0 / 12, -1.0 / 12])
+    interpolate_x(p, f)
+    interpolate_z(p, f)
+    for v in range(4):
+        assert np.allclose(convolve2d(state[v, 2:nz + 2, :], k4[None, :], mode="same")[:, 2:-1], f.vals_x[v])
+        assert np.allclose(convolve2d(state[v, :, 2:nx + 2], k4[:, None], mode="same")[2:-1, :], f.vals_z[v])
+    f.close()
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_unfused_operator_chain_matches_oracle(native):
+    """interpolate -> flux -> tend, both directions, filling fields.vals_*/d3_vals_*/flux/tend like
+    the reference (solve/step.py:67-76 without the fusion)."""
+    from pyminiweather_b200.solve import (compute_flux_x, compute_flux_z, compute_tend_x, compute_tend_z,
+                                          interpolate_x, interpolate_z)
+    if native:
+        p, f, _ = native_fields(52, 26, "collision")
+        _, case = new_case(52, 26, "collision")
+    else:
+        p, case = new_case(52, 26, "collision")
+        f = foreign_fields(case)
+        f.vals_x = np.zeros((4, 26, 53)); f.d3_vals_x = np.zeros((4, 26, 53))
+        f.vals_z = np.zeros((4, 27, 52)); f.d3_vals_z = np.zeros((4, 27, 52))
+        f.flux = np.zeros((4, 27, 53)); f.tend = np.zeros((4, 26, 52))
+    for _ in range(3):
+        no.evolve(case)
+    no.set_bc_x(case, case.state); no.set_bc_z(case, case.state)
+    if native:
+        f.state = case.state.copy()
+    else:
+        f.state[:] = case.state
+    st = f.state
+    # x
+    interpolate_x(p, f, st)
+    vals, d3 = no.interpolate_x(case, case.state)
+    assert np.array_equal(f.vals_x, vals) and np.array_equal(f.d3_vals_x, d3)        # bit-exact
+    compute_flux_x(p, f)
+    fx = no.compute_flux_x(case, vals, d3)
+    assert rel_l2(f.flux[:, :26, :53], fx) <= 1e-15
+    compute_tend_x(p, f, st)
+    want = -(f.flux[:, :26, 1:53] - f.flux[:, :26, 0:52]) / case.dx
+    assert np.array_equal(f.tend, want)                                               # bit-exact given flux
+    # z
+    interpolate_z(p, f, st)
+    vals, d3 = no.interpolate_z(case, case.state)
+    assert np.array_equal(f.vals_z, vals) and np.array_equal(f.d3_vals_z, d3)
+    compute_flux_z(p, f)
+    fz = no.compute_flux_z(case, vals, d3)
+    assert rel_l2(f.flux[:, :27, :52], fz) <= 1e-13   # z flux is a pressure PERTURBATION: pow ulp / cancellation
+    assert not f.d3_vals_z[0, 0].any() and not f.d3_vals_z[0, 26].any()
+    compute_tend_z(p, f, st)
+    want = -(f.flux[:, 1:27, :52] - f.flux[:, 0:26, :52]) / case.dz
+    want[2] -= case.state[0, 2:-2, 2:-2] * no.GRAV
+    assert np.array_equal(f.tend, want)
+
+
+# ---- command-line driver (reference: pyminiweather/__main__.py:183-248) ------------------------------
+def test_cli_driver_end_to_end(tmp_path, caplog):
+    import logging
+    from conftest import golden
+    from pyminiweather_b200.__main__ import main
+    g = golden("evolve_thermal_100x50.npz")
+    out = tmp_path / "dump.txt"
+    with caplog.at_level(logging.INFO, logger="pyminiweather"):
+        rc = main(["--nx", "100", "--nz", "50", "--nsteps", "10", "--output-freq", "5", "--app-filename", str(out)])
+    assert rc == 0
+    text = caplog.text
+    start = [ln for ln in text.splitlines() if "Start: total_mass" in ln][0]
+    end = [ln for ln in text.splitlines() if "End: total_mass" in ln][0]
+    m0, e0 = [float(x) for x in start.split(":")[-1].split(",")]
+    m1, e1 = [float(x) for x in end.split(":")[-1].split(",")]
+    assert abs(m0 - g["stats0"][0]) / m0 <= 1e-12 and abs(e0 - g["stats0"][1]) / e0 <= 1e-12
+    assert abs(m1 - g["stats_10"][0]) / m1 <= 1e-12 and abs(e1 - g["stats_10"][1]) / e1 <= 1e-12
+    # two dumps (before steps 5 and 10), in the reference's text layout: rows of nx+4 comma-separated values
+    dumped = np.loadtxt(out, delimiter=",")
+    assert dumped.shape == (2 * 4 * 54, 104)
+    _, case = new_case(100, 50, "thermal")
+    for _ in range(4):
+        no.evolve(case)
+    first = dumped[:4 * 54].reshape(4, 54, 104)
+    assert worst_rel_l2(first, case.state) <= 1e-11
+    sv = np.loadtxt(str(out).replace(".txt", "_svars.txt"), delimiter=",")
+    assert sv.shape == (2 * 4 * 50, 100)
+    assert rel_l2(sv[:200].reshape(4, 50, 100), no.compute_solution_variables(case)) <= 1e-11
