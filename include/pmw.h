@@ -92,6 +92,10 @@ int pmw_synchronize(pmw_ctx *ctx);
 int pmw_set_hydrostatic(pmw_ctx *ctx, const double *hy_dens_cell, const double *hy_dens_theta_cell,
                         const double *hy_dens_int, const double *hy_dens_theta_int,
                         const double *hy_pressure_int);
+/* ic_type "gravity" only: the constant forcing wpert(x,z)*hy_dens_cell[k] that add_source_terms
+ * (pyminiweather/solve/source.py:43-75, called at solve/step.py:78) adds to the rho*w tendency in
+ * every stage; host [nz][nx], NULL clears it. */
+int pmw_set_source_w(pmw_ctx *ctx, const double *host_nz_nx);
 /* host [4][nz+4][nx+4] <-> device buffer `buf` (PMW_BUF_*).  Synchronous. */
 int pmw_upload_state(pmw_ctx *ctx, int buf, const double *host);
 int pmw_download_state(pmw_ctx *ctx, int buf, double *host);

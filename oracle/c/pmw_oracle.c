@@ -65,6 +65,8 @@ typedef struct {
     const double *hy_pressure_int;    /* [nz+1] */
     double *flux;                     /* scratch [4][nz+1][nx+1] */
     double *tend;                     /* scratch [4][nz][nx]     */
+    const double *source_w;           /* [nz][nx] or NULL: gravity-wave forcing on rho*w in every
+                                         stage (source.py:43-50, step.py:78) */
 } pmwo_case;
 
 #define S(s, v, k, i) (s)[((size_t)(v) * NZ + (size_t)(k)) * NX + (size_t)(i)]
@@ -205,7 +207,11 @@ void pmwo_discrete_step(const pmwo_case *c, const double *init, double *forcing,
     for (int k = 0; k < nz; ++k)
         for (int v = 0; v < 4; ++v)
             for (int i = 0; i < nx; ++i)
-                S(out, v, k + HS, i + HS) = S(init, v, k + HS, i + HS) + dt_stage * T(v, k, i);
+            {
+                double td = T(v, k, i);
+                if (v == WMOM && c->source_w) td += c->source_w[(size_t)k * nx + i];
+                S(out, v, k + HS, i + HS) = S(init, v, k + HS, i + HS) + dt_stage * td;
+            }
 }
 
 /* step.py:105-143; *reverse is the direction flag (module global in the reference) */

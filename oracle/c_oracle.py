@@ -23,7 +23,7 @@ class _Case(C.Structure):
                 ("dx", C.c_double), ("dz", C.c_double), ("dt", C.c_double),
                 ("hy_dens_cell", _dp), ("hy_dens_theta_cell", _dp),
                 ("hy_dens_int", _dp), ("hy_dens_theta_int", _dp), ("hy_pressure_int", _dp),
-                ("flux", _dp), ("tend", _dp)]
+                ("flux", _dp), ("tend", _dp), ("source_w", _dp)]
 
 
 def build(force: bool = False) -> str:
@@ -62,7 +62,8 @@ class COracle:
         self._c = _Case(case.nx, case.nz, case.dx, case.dz, case.dt,
                         _p(case.hy_dens_cell), _p(case.hy_dens_theta_cell),
                         _p(case.hy_dens_int), _p(case.hy_dens_theta_int),
-                        _p(case.hy_pressure_int), _p(self._flux), _p(self._tend))
+                        _p(case.hy_pressure_int), _p(self._flux), _p(self._tend),
+                        _p(case.source_w) if getattr(case, "source_w", None) is not None else None)
 
     def evolve(self, nsteps: int = 1, dt: float | None = None):
         rev = C.c_int(1 if self.case.reverse_direction else 0)

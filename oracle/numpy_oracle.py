@@ -69,6 +69,9 @@ class OracleCase:
     hy_pressure_int: np.ndarray
     # step.py:18 is a module global in the reference; here it is per case.
     reverse_direction: bool = False
+    # ic_type == "gravity" only: wpert(x,z) * hy_dens_cell[2:nz+2, None], added to the w-momentum
+    # tendency in EVERY stage, both directions (source.py:43-50, called at step.py:78)
+    source_w: np.ndarray | None = None
     scratch: dict = field(default_factory=dict)
 
     def copy(self) -> "OracleCase":
@@ -78,6 +81,7 @@ class OracleCase:
             self.hy_dens_cell.copy(), self.hy_dens_theta_cell.copy(),
             self.hy_dens_int.copy(), self.hy_dens_theta_int.copy(),
             self.hy_pressure_int.copy(), self.reverse_direction,
+            None if self.source_w is None else self.source_w.copy(),
         )
 
 
@@ -215,6 +219,8 @@ def discrete_step(case: OracleCase, init: np.ndarray, forcing: np.ndarray,
     fully materialised before the update, exactly as in the reference)."""
     nx, nz = case.nx, case.nz
     tend = tendency(case, forcing, direction)
+    if case.source_w is not None:  # add_source_terms, source.py:53-75
+        tend[WMOM] += case.source_w
     out[:, HS:nz + HS, HS:nx + HS] = init[:, HS:nz + HS, HS:nx + HS] + dt * tend
 
 
@@ -228,6 +234,20 @@ def evolve(case: OracleCase, dt: float | None = None) -> None:
         discrete_step(case, case.state, case.state_tmp, case.state_tmp, dt / 2, d)
         discrete_step(case, case.state, case.state_tmp, case.state, dt / 1, d)
     case.reverse_direction = not case.reverse_direction
+
+
+def gravity_source(nx, nz, dx, dz, xlen, zlen, hy_dens_cell) -> np.ndarray:
+    """The gravity-wave forcing field of source.py:41-50: a squared-cosine bump of amplitude 0.01
+    centred at (xlen/8, 1000 m), radii 500 m, sampled at cell centres (mesh.py:55-77,
+    utils/utils.py:40-51), times the hydrostatic density of the row."""
+    x = np.linspace(dx / 2.0, xlen + dx / 2.0, nx, endpoint=False)
+    z = np.linspace(dz / 2.0, zlen + dz / 2.0, nz, endpoint=False)
+    x, z = np.meshgrid(x, z)
+    pi = 3.14159265358979323846264338327
+    dist = np.sqrt(((x - xlen / 8) / 500.0) ** 2 + ((z - 1000.0) / 500.0) ** 2) * pi / 2.0
+    wpert = np.zeros(z.shape)
+    np.putmask(wpert, dist <= pi / 2.0, 0.01 * (np.cos(dist) ** 2.0))
+    return wpert * hy_dens_cell[HS:nz + HS, np.newaxis]
 
 
 # ---- diagnostics ----------------------------------------------------------------------

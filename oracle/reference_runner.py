@@ -91,8 +91,12 @@ class ReferenceRun:
 
     def to_oracle_case(self):
         """Snapshot the current reference arrays into an ``OracleCase``."""
-        from .numpy_oracle import OracleCase
+        from .numpy_oracle import OracleCase, gravity_source
         f, p = self.fields, self.params
+        src = None
+        if p["ic_type"] == "gravity":
+            src = gravity_source(p["nx"], p["nz"], float(p["dx"]), float(p["dz"]), p["xlen"], p["zlen"],
+                                 np.asarray(f.hy_dens_cell))
         return OracleCase(
             nx=p["nx"], nz=p["nz"], dx=float(p["dx"]), dz=float(p["dz"]), dt=float(p["dt"]),
             state=np.array(f.state, copy=True), state_tmp=np.array(f.state_tmp, copy=True),
@@ -101,5 +105,5 @@ class ReferenceRun:
             hy_dens_int=np.array(f.hy_dens_int, copy=True),
             hy_dens_theta_int=np.array(f.hy_dens_theta_int, copy=True),
             hy_pressure_int=np.array(f.hy_pressure_int, copy=True),
-            reverse_direction=self._reverse,
+            reverse_direction=self._reverse, source_w=src,
         )

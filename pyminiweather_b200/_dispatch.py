@@ -22,16 +22,28 @@ from .engine import HYDRO_NAMES, DeviceSolver
 _foreign: dict[int, tuple] = {}
 _MAX_FOREIGN = 4  # contexts kept alive for foreign fields objects
 
-UNSUPPORTED_ICS = ("injection", "gravity")
+UNSUPPORTED_ICS = ("injection",)
 
 
 def check_ic(ic_type):
-    """The injection inflow BC (bcs.py:37,41-64) and the gravity-wave source term
-    (source.py:20-50) are not part of the accelerated path yet."""
+    """The injection inflow BC (bcs.py:37,41-64: non-periodic x halos with forced inflow rows) is not
+    part of the accelerated path (the reference's README lists it as unsupported, README.md:291)."""
     if ic_type in UNSUPPORTED_ICS:
         raise NotImplementedError(
             f"ic_type={ic_type!r} is not supported by the B200 hot path (periodic-x / solid-wall-z "
-            "configurations only: thermal, collision, density-current)")
+            "configurations only: thermal, collision, density-current, gravity)")
+
+
+def sync_source(solver, params, hy_dens_cell):
+    """Upload (or clear) the extra rho*w forcing of the configuration (solve/source.py)."""
+    from .solve.source import source_field_for
+    want = source_field_for(params, hy_dens_cell) if np.all(np.asarray(hy_dens_cell) > 0) else None
+    have = getattr(solver, "_source", None)
+    if want is None:
+        if have is not None:
+            solver.set_source_w(None)
+    elif have is None or not np.array_equal(have, want):
+        solver.set_source_w(want)
 
 
 def direction_id(direction) -> int:
@@ -69,6 +81,7 @@ def foreign_solver(fields, params) -> DeviceSolver:
     hydro = [np.ascontiguousarray(getattr(fields, n), dtype=np.float64) for n in HYDRO_NAMES]
     if all(np.all(h > 0) for h in hydro[:4]) and not solver.hydro_matches(hydro):
         solver.set_hydrostatic(*hydro)
+    sync_source(solver, params, hydro[0])
     return solver
 
 

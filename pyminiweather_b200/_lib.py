@@ -46,6 +46,7 @@ SIGNATURES = {
     "pmw_set_stream": (C.c_int, [_vp, _vp]),
     "pmw_synchronize": (C.c_int, [_vp]),
     "pmw_set_hydrostatic": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "pmw_set_source_w": (C.c_int, [_vp, _vp]),
     "pmw_upload_state": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_download_state": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_upload_state_async": (C.c_int, [_vp, C.c_int, _vp]),

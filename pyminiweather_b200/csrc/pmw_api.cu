@@ -72,6 +72,7 @@ struct pmw_ctx {
     int spare;
     bool xhalo_valid[3];  // x halo columns hold the periodic image of the interior
     double* hydro_blob;
+    double* src_w;  // gravity-wave forcing field or nullptr
     Hydro hy;
     bool hydro_set;
     cudaStream_t stream;
@@ -149,6 +150,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->buf_doubles = (size_t)NVAR * c->L.vstride + 32;
     for (int b = 0; b < 3; ++b) c->alloc[b] = nullptr;
     c->hydro_blob = nullptr;
+    c->src_w = nullptr;
     c->stats_partial = c->stats_out = nullptr;
     c->flags = nullptr;
     c->edge_counters = nullptr;
@@ -216,6 +218,7 @@ extern "C" int pmw_destroy(pmw_ctx* c)
     for (int b = 0; b < 3; ++b)
         if (c->alloc[b]) cudaFree(c->alloc[b]);
     if (c->hydro_blob) cudaFree(c->hydro_blob);
+    if (c->src_w) cudaFree(c->src_w);
     if (c->stats_partial) cudaFree(c->stats_partial);
     if (c->stats_out) cudaFree(c->stats_out);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -324,6 +327,21 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
     c->hy.pressure_int = d;             d += nint;
     c->hy.inv_dens_theta_int = d;
     c->hydro_set = true;
+    return PMW_OK;
+}
+
+extern "C" int pmw_set_source_w(pmw_ctx* c, const double* host)
+{
+    BIND(c);
+    if (!host) {
+        if (c->src_w) cudaFree(c->src_w);
+        c->src_w = nullptr;
+        return PMW_OK;
+    }
+    const size_t n = (size_t)c->p.nx * c->p.nz;
+    if (!c->src_w) CU_TRY(cudaMalloc(&c->src_w, n * sizeof(double)));
+    CU_TRY(cudaMemcpyAsync(c->src_w, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
     return PMW_OK;
 }
 
@@ -560,6 +578,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
         a.hint_out = h % 10;
     }
     a.hy = c->hy;
+    a.src_w = c->src_w;
     const double d = (direction == PMW_DIR_X) ? c->p.dx : c->p.dz;
     a.hv_coeff = -HV_BETA * d / (16 * c->p.dt);
     a.inv_d = 1.0 / d;

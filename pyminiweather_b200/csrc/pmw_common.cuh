@@ -62,6 +62,7 @@ struct StageArgs {
     double* out_left;   // same logical buffer on the left  slab neighbour (== out when periodic_x)
     double* out_right;  // same logical buffer on the right slab neighbour
     Hydro hy;
+    const double* src_w;  // [nz][nx] extra rho*w tendency (ic_type "gravity", source.py:43-50) or nullptr
     double hv_coeff;  // -hv_beta*d/(16*dt_full)   (interpolate.py:101,149)
     double inv_d;     // 1/dx or 1/dz
     double dt_stage;

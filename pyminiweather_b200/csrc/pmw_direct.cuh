@@ -96,7 +96,8 @@ __device__ __forceinline__ void stage_x_direct_cell(const StageArgs& a, int i, i
     interface_flux<false, POW_MODE>(s[1], s[2], s[3], s[4], bg, a.hv_coeff, false, fr);
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        const double tend = (fl[v] - fr[v]) * a.inv_d;
+        double tend = (fl[v] - fr[v]) * a.inv_d;
+        if (v == WMOM && a.src_w) tend += __ldg(a.src_w + (long long)k * a.L.nx + i);
         const double ini = (a.init == a.forcing) ? s[2][v] : __ldg(a.init + idx(a.L, v, k + HS, i + HS));
         store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
     }
@@ -141,7 +142,10 @@ __device__ __forceinline__ void stage_z_direct_cell(const StageArgs& a, int i, i
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         double tend = (fb[v] - ft[v]) * a.inv_d;
-        if (v == WMOM) tend = fma(-s[2][DENS], GRAV, tend);  // interpolate.py:248-250
+        if (v == WMOM) {
+            tend = fma(-s[2][DENS], GRAV, tend);  // interpolate.py:248-250
+            if (a.src_w) tend += __ldg(a.src_w + (long long)k * a.L.nx + i);
+        }
         const double ini = (a.init == a.forcing) ? s[2][v] : __ldg(a.init + idx(a.L, v, k + HS, i + HS));
         store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
     }

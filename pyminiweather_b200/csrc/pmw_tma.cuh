@@ -250,8 +250,13 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
                 } else {
                     ia = t2[v]; ib = t3[v];
                 }
-                const double xa = fma(a.dt_stage, (f0[v] - f1[v]) * a.inv_d, ia);
-                const double xb = fma(a.dt_stage, (f1[v] - fr) * a.inv_d, ib);
+                double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                if (v == WMOM && a.src_w) {  // gravity-wave forcing (source.py:43-50)
+                    const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)k * nx + i));
+                    ta += g.x; tb += g.y;
+                }
+                const double xa = fma(a.dt_stage, ta, ia);
+                const double xb = fma(a.dt_stage, tb, ib);
                 store_pair(a, po + 64 * q, v * a.L.vstride, edge, i, xa, xb, pol_out);
             }
         }
@@ -405,6 +410,10 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
                 if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250); cell kf is tap 2
                     ta = fma(-a2[DENS], GRAV, ta);
                     tb = fma(-b2[DENS], GRAV, tb);
+                    if (a.src_w) {  // gravity-wave forcing (source.py:43-50)
+                        const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)kf * nx + i));
+                        ta += g.x; tb += g.y;
+                    }
                 }
                 const double ia = HAS_INIT ? ini[v].a : a2[v];
                 const double ib = HAS_INIT ? ini[v].b : b2[v];

@@ -98,12 +98,18 @@ class Fields:
                 self._solver.close()
             self._solver = DeviceSolver(key[0], key[1], key[3], key[4], key[5], hs=key[2])
             self._solver_key = key
+            self._source_ic = None
             self._host_dirty = {PMW_BUF_STATE: True, PMW_BUF_TMP: True}
         hydro = [getattr(self, n) for n in HYDRO_NAMES]
         # profiles still all-zero (init() not run yet): leave them unset -- operators that need them
         # then fail with "hydrostatic profiles not set", the pure stencil shims work regardless
         if all(np.all(h > 0) for h in hydro[:4]) and not self._solver.hydro_matches(hydro):
             self._solver.set_hydrostatic(*hydro)
+        ic = params.get("ic_type")
+        if ic != self.__dict__.get("_source_ic"):  # the forcing field only depends on the configuration
+            from .._dispatch import sync_source
+            sync_source(self._solver, params, self.hy_dens_cell)
+            self._source_ic = ic if np.all(self.hy_dens_cell > 0) else None
         for buf in (PMW_BUF_STATE, PMW_BUF_TMP):
             if self._host_dirty[buf]:
                 self._solver.upload(buf, self._host[buf])

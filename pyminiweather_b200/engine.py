@@ -57,6 +57,7 @@ class DeviceSolver:
         self._h = h
         self._lib = lib
         self._hydro = None
+        self._source = None
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -86,6 +87,16 @@ class DeviceSolver:
         dp = C.POINTER(C.c_double)
         check(self._lib.pmw_set_hydrostatic(self._h, *[a.ctypes.data_as(dp) for a in arrs]))
         self._hydro = [a.copy() for a in arrs]
+
+    def set_source_w(self, field):
+        """Gravity-wave forcing on rho*w ([nz, nx]) or None to clear it."""
+        if field is None:
+            check(self._lib.pmw_set_source_w(self._h, None))
+            self._source = None
+            return
+        field = _as_f64(field, (self.nz, self.nx), "source_w")
+        check(self._lib.pmw_set_source_w(self._h, C.c_void_p(field.ctypes.data)))
+        self._source = field.copy()
 
     def hydro_matches(self, arrs) -> bool:
         return self._hydro is not None and all(np.array_equal(a, b) for a, b in zip(self._hydro, arrs))

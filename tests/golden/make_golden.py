@@ -95,3 +95,16 @@ save("evolve_thermal_512x256_5steps_sub8.npz", sub=inner[:, ::8, ::8].copy(),
 
 with open(os.path.join(HERE, "manifest.json"), "w") as fh:
     json.dump(manifest, fh, indent=1, sort_keys=True)
+
+# 6. gravity-wave configuration (extra w-momentum source in every stage, source.py:20-50)
+r = rr.ReferenceRun(100, 50, "gravity")
+out = dict(state0=r.fields.state.copy(), stats0=np.array(r.stats()), **hydro(r.fields), **scal(r.params))
+done = 0
+for n in (1, 2, 20):
+    r.evolve(n - done)
+    done = n
+    out[f"state_{n}"] = r.fields.state.copy()
+    out[f"stats_{n}"] = np.array(r.stats())
+save("evolve_gravity_100x50.npz", **out)
+with open(os.path.join(HERE, "manifest.json"), "w") as fh:
+    json.dump(manifest, fh, indent=1, sort_keys=True)

@@ -47,7 +47,10 @@ def new_case(nx, nz, ic_type="thermal", **kw):
     f = initialize_fields(p)
     init(f, p, MeshData(p))
     hydro = {n: getattr(f, n) for n in HYDRO}
-    return p, case_from_arrays(p, f._host[0], f._host[1], hydro)
+    case = case_from_arrays(p, f._host[0], f._host[1], hydro)
+    if ic_type == "gravity":
+        case.source_w = no.gravity_source(nx, nz, case.dx, case.dz, p["xlen"], p["zlen"], case.hy_dens_cell)
+    return p, case
 
 
 def synthetic_case(nx, nz, seed=20260101):

@@ -135,9 +135,8 @@ def test_unsupported_configurations_raise():
     from pyminiweather_b200.engine import DeviceSolver
     from pyminiweather_b200.solve import evolve
     p, f, mesh = native_fields(32, 16, "thermal")
-    for ic in ("injection", "gravity"):
-        with pytest.raises(NotImplementedError):
-            evolve(dict(p, ic_type=ic), f, mesh, dt=p["dt"])
+    with pytest.raises(NotImplementedError):
+        evolve(dict(p, ic_type="injection"), f, mesh, dt=p["dt"])
     with pytest.raises(PmwError, match="hs must be 2"):
         DeviceSolver(32, 16, 1.0, 1.0, 0.1, hs=3)
     with pytest.raises(PmwError, match=">= 4"):
@@ -148,6 +147,28 @@ def test_unsupported_configurations_raise():
     with pytest.raises(ValueError):
         s.upload(0, np.zeros((4, 20, 35)))
     s.close()
+
+
+def test_gravity_through_the_operator_api():
+    """The source field is built and uploaded by the operators themselves from params/fields."""
+    from pyminiweather_b200.post import compute_stats
+    from pyminiweather_b200.solve import evolve
+    p, f, mesh = native_fields(100, 50, "gravity")
+    _, case = new_case(100, 50, "gravity")
+    for _ in range(8):
+        evolve(p, f, mesh, dt=p["dt"])
+        no.evolve(case)
+    assert worst_rel_l2(f.state, case.state) <= 1e-11
+    m, e = compute_stats(p, f)
+    mo, eo = no.compute_stats(case)
+    assert abs(m - mo) / mo <= 1e-12 and abs(e - eo) / eo <= 1e-12
+    f.close()
+    ff = foreign_fields(new_case(100, 50, "gravity")[1])
+    _, c2 = new_case(100, 50, "gravity")
+    for _ in range(2):
+        evolve(p, ff, None, dt=p["dt"])
+        no.evolve(c2)
+    assert worst_rel_l2(ff.state, c2.state) <= 1e-11
 
 
 # ---- unfused operator shims (reference: pyminiweather/solve/interpolate.py) ------------------------

@@ -100,6 +100,23 @@ def test_evolve_100_steps_other_ics(ic):
     s.close()
 
 
+def test_evolve_gravity_configuration():
+    """ic_type 'gravity' (SURVEY 8f): Brunt-Vaisala background, uniform wind, and the constant
+    rho*w forcing of add_source_terms applied inside the fused kernels in every stage."""
+    g = golden("evolve_gravity_100x50.npz")
+    for variant in ("tma", "direct"):
+        p, case = case_from_golden(g, "state0", ic_type="gravity")
+        s = solver_for(case, variant)
+        s.set_source_w(no.gravity_source(100, 50, case.dx, case.dz, 2e4, 1e4, case.hy_dens_cell))
+        done = 0
+        for n in (1, 2, 20):
+            s.evolve(n - done)
+            done = n
+            assert worst_rel_l2(s.download(STATE), g[f"state_{n}"]) <= STATE_TOL, (variant, n)
+            assert_stats(s.stats(STATE), g[f"stats_{n}"])
+        s.close()
+
+
 # ---- ragged / odd grids against the NumPy oracle (tile edges, tiny grids) -----------------------
 @pytest.mark.parametrize("variant", ["direct", "tma"])
 @pytest.mark.parametrize("nx,nz", [(4, 4), (5, 7), (6, 5), (37, 19), (62, 9), (126, 70), (130, 70), (257, 33), (160, 16), (318, 65)])

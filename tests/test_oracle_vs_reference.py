@@ -8,6 +8,8 @@ import textwrap
 import numpy as np
 import pytest
 
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import numpy_oracle as no, reference_runner as rr
 
 pytestmark = pytest.mark.skipif(not rr.available(), reason="/root/reference not mounted")
@@ -55,3 +57,20 @@ def test_reference_own_unit_tests_pass_with_numpy_shim(tmp_path):
                           os.path.join(rr.REFERENCE_ROOT, "tests/unit/test_constants.py")],
                          env=env, capture_output=True, text=True, cwd=str(tmp_path))
     assert res.returncode == 0, res.stdout + res.stderr
+
+
+def test_gravity_source_restatement_matches_reference():
+    ref = rr.ReferenceRun(64, 32, "gravity")
+    case = ref.to_oracle_case()
+    from pyminiweather.utils import sample_ellipse_cosine  # reference
+    x, z = ref.mesh.get_mesh_cell_centers()
+    want = sample_ellipse_cosine(x, z, 0.01, ref.params["xlen"] / 8, 1000.0, 500.0, 500.0) * \
+        ref.fields.hy_dens_cell[2:34, None]
+    assert np.array_equal(case.source_w, want)
+    from helpers import make_params
+    from pyminiweather_b200.solve.source import gravity_source_field
+    assert np.array_equal(gravity_source_field(make_params(64, 32, "gravity"), ref.fields.hy_dens_cell), want)
+    for _ in range(6):
+        ref.evolve(1)
+        no.evolve(case)
+    assert np.array_equal(ref.fields.state, case.state)
