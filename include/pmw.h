@@ -176,7 +176,11 @@ int pmw_peer_status(pmw_ctx *ctx, int *timed_out);
  * Tile shapes of the TMA variant.  Keys: "x_tr" (rows per x tile: 4|8), "x_p" (passes of 64
  * interfaces per x tile row, 1..3; a tile owns 64*x_p-2 cells per row), "z_cfg" (passes of 4
  * interface rows per z tile, 1..8; a tile owns 4*z_cfg-1 cell rows x 64 columns), "pdl"
- * (0|1: programmatic dependent launch between consecutive stage kernels; default 1). */
+ * (0|1: programmatic dependent launch between consecutive stage kernels; default 1), "l2_hints"
+ * (decimal abcd = L2 eviction priority of: forcing in stage 1, forcing in stages 2-3, init, out;
+ * 0 normal, 1 evict_first, 2 evict_last; default 1100), "chain" (0|1, default 0: experimental
+ * tile-level dependency flags between consecutive stages instead of whole-grid waits -- measured
+ * slower than PDL alone, kept for study), "peer_dbg" (development switches). */
 int pmw_set_tuning(pmw_ctx *ctx, const char *key, int value);
 int pmw_get_tuning(pmw_ctx *ctx, const char *key, int *value);
 

@@ -95,6 +95,13 @@ struct pmw_ctx {
     unsigned int* edge_counters;     // last-arriver counter of the push CTAs
     unsigned long long epoch;        // number of x stages run since pmw_connect_peers
     std::vector<void*> ipc_opened;
+    // tile-level chaining of consecutive fused stage kernels
+    unsigned int* tile_flags[8];  // ring over stages: a word is rewritten 8 stages later at the earliest
+    size_t tile_flags_len;
+    unsigned int stage_epoch;
+    bool chain_valid;
+    int chain_tc, chain_tr, chain_ntx;
+    int chain;  // tuning: 0 = always wait for the whole previous grid
     // bookkeeping
     long long launches;
     bool timing;
@@ -154,6 +161,10 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->stats_partial = c->stats_out = nullptr;
     c->flags = nullptr;
     c->edge_counters = nullptr;
+    for (int b = 0; b < 8; ++b) c->tile_flags[b] = nullptr;
+    c->stage_epoch = 0;
+    c->chain_valid = false;
+    c->chain = 0;  // measured slower than PDL alone on B200: a gpu-scope release per CTA costs more than the tail it hides
     c->peers = false;
     c->epoch = 0;
     for (int b = 0; b < 3; ++b) {
@@ -192,6 +203,14 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
             cudaMalloc(&c->flags, 4 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(c->flags, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&c->edge_counters, 2 * sizeof(unsigned int)) != cudaSuccess ||
+            [&]() {  // one completion word per tile of the finest tiling either stage kernel can use
+                c->tile_flags_len = (size_t)((params->nx + 61) / 62 + 1) * ((params->nz + 2) / 3 + 1);
+                for (int b = 0; b < 8; ++b)
+                    if (cudaMalloc(&c->tile_flags[b], c->tile_flags_len * sizeof(unsigned int)) != cudaSuccess ||
+                        cudaMemset(c->tile_flags[b], 0, c->tile_flags_len * sizeof(unsigned int)) != cudaSuccess)
+                        return true;
+                return false;
+            }() ||
             cudaMemset(c->edge_counters, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
             pmw_destroy(c);
             return fail(PMW_ECUDA, "cudaMalloc of auxiliary buffers failed");
@@ -224,6 +243,8 @@ extern "C" int pmw_destroy(pmw_ctx* c)
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->flags) cudaFree(c->flags);
     if (c->edge_counters) cudaFree(c->edge_counters);
+    for (int b = 0; b < 8; ++b)
+        if (c->tile_flags[b]) cudaFree(c->tile_flags[b]);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     delete c;
     return PMW_OK;
@@ -246,6 +267,7 @@ extern "C" int pmw_synchronize(pmw_ctx* c)
 extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
 {
     BIND(c);
+    c->chain_valid = false;
     NEED(key, "pmw_set_tuning: null key");
     if (!strcmp(key, "x_tr")) {
         NEED(value == 4 || value == 8, "x_tr must be 4 or 8");
@@ -262,6 +284,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         c->peer_dbg = value;
     } else if (!strcmp(key, "l2_hints")) {
         c->l2_hints = value;
+    } else if (!strcmp(key, "chain")) {
+        c->chain = value ? 1 : 0;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -364,6 +388,7 @@ static int copy_state(pmw_ctx* c, int buf, double* host, bool to_device, bool sy
     const size_t NX = c->p.nx + 4, rows = (size_t)NVAR * (c->p.nz + 4);
     double* dev = c->base[c->l2p[buf]];
     if (to_device) {
+        c->chain_valid = false;
         CU_TRY(cudaMemcpy2DAsync(dev, c->L.pitch * sizeof(double), host, NX * sizeof(double), NX * sizeof(double),
                                  rows, cudaMemcpyHostToDevice, c->stream));
         c->xhalo_valid[c->l2p[buf]] = false;
@@ -420,6 +445,7 @@ static int after_launch(pmw_ctx* c, const char* what)
 extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
 {
     BIND(c);
+    c->chain_valid = false;
     CHECK_BUF(buf);
     const int n = NVAR * c->p.nz;
     bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L);
@@ -431,6 +457,7 @@ extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
 extern "C" int pmw_bc_z(pmw_ctx* c, int buf)
 {
     BIND(c);
+    c->chain_valid = false;
     CHECK_BUF(buf);
     NEED(c->hydro_set, "pmw_bc_z: hydrostatic profiles not set");
     const int n = c->p.nx + 4;
@@ -519,13 +546,13 @@ static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
 {
     using T = ZTile<NP>;
     const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + T::TR - 1) / T::TR);
-    const size_t smem = T::smem_bytes();
+    const size_t smem = T::smem_bytes(has_init);
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
 #define GO(HI, PM)                                                                 \
     do {                                                                           \
         static unsigned long long attr_done = 0; /* one bit per device */           \
         if (!(attr_done >> c->p.device & 1ull)) {                                  \
-            int rc_ = set_smem(stage_z_tma<NP, HI, PM>, T::smem_bytes());          \
+            int rc_ = set_smem(stage_z_tma<NP, HI, PM>, T::smem_bytes(true));      \
             if (rc_ != PMW_OK) return rc_;                                         \
             attr_done |= 1ull << c->p.device;                                      \
         }                                                                          \
@@ -569,6 +596,11 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.nbr_forcing_left = a.nbr_forcing_right = nullptr;
     a.nbr_flags_left = a.nbr_flags_right = nullptr;
     a.push_counter = c->edge_counters;
+    a.tile_flags_out = nullptr;
+    a.prod_flags = nullptr;
+    a.epoch_out = a.epoch_in = 0;
+    a.prod_tc = a.prod_tr = a.prod_ntx = 1;
+    a.chain_wrap = c->p.periodic_x;
     a.dbg = c->peer_dbg;
     {   // l2_hints = decimal "abcd": a = forcing when init==forcing (stage 1), b = forcing otherwise,
         // c = init, d = out; each 0 normal | 1 evict_first | 2 evict_last
@@ -615,6 +647,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     }
 
     if (c->p.variant == PMW_VARIANT_DIRECT || (c->p.nx & 1)) {  // the TMA kernels pair cells in x
+        c->chain_valid = false;
         const dim3 block(64, 4);
         const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4 + (direction == PMW_DIR_X ? push_rows : 0));
         const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
@@ -628,6 +661,24 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     } else {
         const CUtensorMap *tf = nullptr, *ti = nullptr;
         int rc;
+        // tile-level chaining with the previous fused stage kernel
+        const int my_tc = (direction == PMW_DIR_X) ? 64 * c->x_p - 2 : 64;
+        const int my_tr = (direction == PMW_DIR_X) ? c->x_tr : 4 * c->z_cfg - 1;
+        const int my_ntx = (c->p.nx + my_tc - 1) / my_tc;
+        const unsigned int e = ++c->stage_epoch;
+        a.tile_flags_out = c->chain ? c->tile_flags[e % 8] : nullptr;
+        a.epoch_out = e;
+        if (c->chain && c->chain_valid && fuse_bc_z) {
+            a.prod_flags = c->tile_flags[(e - 1) % 8];
+            a.epoch_in = e - 1;
+            a.prod_tc = c->chain_tc;
+            a.prod_tr = c->chain_tr;
+            a.prod_ntx = c->chain_ntx;
+        }
+        c->chain_valid = fuse_bc_z && c->chain;
+        c->chain_tc = my_tc;
+        c->chain_tr = my_tr;
+        c->chain_ntx = my_ntx;
         if (direction == PMW_DIR_X) {
             const int fw = 64 * c->x_p + 4, iw = 64 * c->x_p;
             if ((rc = get_tmap(c, p_forcing, fw, c->x_tr, &tf)) != PMW_OK) return rc;
@@ -835,6 +886,7 @@ extern "C" int pmw_pack_halo_x(pmw_ctx* c, int buf, double* to_left, double* to_
 extern "C" int pmw_unpack_halo_x(pmw_ctx* c, int buf, const double* from_left, const double* from_right)
 {
     BIND(c);
+    c->chain_valid = false;
     CHECK_BUF(buf);
     NEED(from_left && from_right, "pmw_unpack_halo_x: null message buffer");
     const int n = NVAR * c->p.nz * 2;
@@ -913,6 +965,7 @@ extern "C" int pmw_local_ptrs(pmw_ctx* c, void* ptrs_out[4])
 extern "C" int pmw_connect_peers(pmw_ctx* c, void* const left[4], void* const right[4])
 {
     BIND(c);
+    c->chain_valid = false;
     NEED(!c->p.periodic_x, "pmw_connect_peers: the context was created with periodic_x=1");
     NEED((c->p.nx & 1) == 0, "pmw_connect_peers: the slab width must be even");
     NEED(left && right, "pmw_connect_peers: null argument");

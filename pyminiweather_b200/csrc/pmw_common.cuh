@@ -86,6 +86,15 @@ struct StageArgs {
     int dbg;  // development switches (pmw_set_tuning "peer_dbg"); 0 in production
     // L2 eviction priority per operand: 0 normal, 1 evict_first, 2 evict_last (createpolicy)
     int hint_forcing, hint_init, hint_out;
+    // Tile-level chaining of consecutive stage kernels (see wait_producer_tiles): every CTA publishes
+    // tile_flags_out[tile] = epoch_out when its stores are done; when prod_flags != nullptr a CTA
+    // waits only for the producer tiles its own tile depends on instead of for the whole previous
+    // grid (griddepcontrol.wait), so the head of stage n+1 overlaps the tail of stage n.
+    unsigned int* tile_flags_out;
+    const unsigned int* prod_flags;
+    unsigned int epoch_out, epoch_in;
+    int prod_tc, prod_tr, prod_ntx;  // producer tile size in cells (x, z) and tiles per row
+    int chain_wrap;                  // periodic domain: halo columns are images stored by the edge tiles
 };
 
 __device__ __forceinline__ unsigned long long l2_policy(int kind)

@@ -102,6 +102,52 @@ __device__ __forceinline__ void wait_epoch(unsigned long long* flags, int which,
     asm volatile("fence.proxy.async;" ::: "memory");  // order the acquire before the TMA (async proxy) reads
 }
 
+// Tile-level dependency wait (one thread per CTA).  The tile covering cells [c_lo, c_hi] x
+// [r_lo, r_hi] of the consumer stage may start once every producer-stage tile that
+//   - wrote a cell this tile reads (its own cells plus the 2-cell stencil halo), or
+//   - read a cell this tile overwrites (the producer's stencil halo)
+// has published its epoch.  Both conditions are covered by waiting for the producer tiles that
+// intersect the tile grown by 2 cells on every side; in a periodic domain columns beyond the edge
+// are images stored by the producer tiles that own the opposite edge.
+__device__ __forceinline__ void poll_tile(const StageArgs& a, int ptx, int pty)
+{
+    const unsigned int* f = a.prod_flags + (long long)pty * a.prod_ntx + ptx;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - a.epoch_in) >= 0) break;
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s watchdog: flag an error instead of hanging
+            a.flags[2] = 2ull;
+            break;
+        }
+    } while (true);
+}
+__device__ __forceinline__ void wait_producer_tiles(const StageArgs& a, int c_lo, int c_hi, int r_lo, int r_hi)
+{
+    const int nx = a.L.nx, nz = a.L.nz;
+    c_lo -= 2; c_hi += 2; r_lo -= 2; r_hi += 2;
+    const int ty0 = max(r_lo, 0) / a.prod_tr, ty1 = min(r_hi, nz - 1) / a.prod_tr;
+    const int tx0 = max(c_lo, 0) / a.prod_tc, tx1 = min(c_hi, nx - 1) / a.prod_tc;
+    for (int pty = ty0; pty <= ty1; ++pty) {
+        for (int ptx = tx0; ptx <= tx1; ++ptx) poll_tile(a, ptx, pty);
+        if (a.chain_wrap) {
+            if (c_lo < 0) poll_tile(a, (nx - 1) / a.prod_tc, pty);
+            if (c_hi > nx - 1) poll_tile(a, 0, pty);
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // acquire (generic proxy) before the TMA reads
+}
+// Publish this tile's completion: all stores of the CTA are ordered before the flag by the barrier
+// plus a gpu-scope release by one thread (the CUTLASS semaphore pattern).
+__device__ __forceinline__ void publish_tile(const StageArgs& a, int tile_id)
+{
+    if (!a.tile_flags_out) return;  // chaining off (the default: see pmw_set_tuning "chain")
+    __syncthreads();
+    if (threadIdx.x == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.tile_flags_out + tile_id), "r"(a.epoch_out) : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -198,8 +244,13 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
         mbar_init(bar, 1);
     }
     __syncthreads();
-    pdl_wait();  // everything below reads or overwrites state produced by the previous stage
+    // Everything below reads or overwrites state produced by the previous stage: wait for the whole
+    // previous grid, or -- chained -- only for the producer tiles this tile depends on (thread 0 is
+    // the only thread that touches global memory before the mbarrier wait).
+    if (!a.prod_flags) pdl_wait();
     if (threadIdx.x == 0) {
+        if (a.prod_flags)
+            wait_producer_tiles(a, c0, min(c0 + T::TC, a.L.nx) - 1, r0, min(r0 + TR, a.L.nz) - 1);
         if (a.wait_epoch && !(a.dbg & 2)) {
             if (tx == 0) wait_epoch(a.flags, 0, a.wait_epoch);
             if (tx == ntx - 1) wait_epoch(a.flags, 1, a.wait_epoch);
@@ -261,6 +312,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
             }
         }
     }
+    publish_tile(a, ty * ntx + tx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -284,12 +336,16 @@ struct ZTile {
     static constexpr int X_ELEMS = NVAR * W * TC;      // flux exchange slot of the top pass (the other
                                                        // passes reuse tile rows that are already dead)
     static constexpr int H_ELEMS = 4 * W * NP;         // hydrostatic interface profiles of the tile
+    static constexpr int I_ELEMS = 2 * NVAR * W * TC;  // initial state of two passes (cp.async ring)
     static constexpr int THREADS = 32 * W;
-    static constexpr size_t smem_bytes() { return (size_t)(F_ELEMS + X_ELEMS + H_ELEMS) * sizeof(double) + 16; }
+    static constexpr size_t smem_bytes(bool has_init)
+    {
+        return (size_t)(F_ELEMS + X_ELEMS + H_ELEMS + (has_init ? I_ELEMS : 0)) * sizeof(double) + 16;
+    }
 };
 
 template <int NP, bool HAS_INIT, int POW_MODE>
-__global__ void __launch_bounds__(128, HAS_INIT ? 4 : 5)  // 5 CTAs/SM would spill the init registers
+__global__ void __launch_bounds__(128, HAS_INIT ? 4 : 5)
 stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
 {
     using T = ZTile<NP>;
@@ -298,7 +354,8 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
     double* sF = reinterpret_cast<double*>(smem_raw);
     double* sX = sF + T::F_ELEMS;
     double* sH = sX + T::X_ELEMS;  // [4][W*NP]: dens, dens_theta, 1/dens_theta, pressure per interface row
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sH + T::H_ELEMS);
+    double* sIn = sH + T::H_ELEMS;  // [2][4][W][TC]: initial state of the pass in flight and the next one
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sIn + (HAS_INIT ? T::I_ELEMS : 0));
 
     const int nz = a.L.nz, nx = a.L.nx;
     const int c0 = blockIdx.x * TC;
@@ -316,7 +373,15 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
         sH[3 * W * NP + threadIdx.x] = __ldg(a.hy.pressure_int + kc);
     }
     __syncthreads();
-    pdl_wait();  // everything below reads or overwrites state produced by the previous stage
+    // wait for the previous stage: the whole grid, or (chained) the producer tiles of this tile; all
+    // threads read `init` below, so the chained wait is followed by a block barrier
+    if (!a.prod_flags) {
+        pdl_wait();
+    } else {
+        if (threadIdx.x == 0)
+            wait_producer_tiles(a, c0, min(c0 + TC, nx) - 1, r0, min(r0 + T::TR, nz) - 1);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar, (uint32_t)(T::F_ELEMS * sizeof(double)));
         tma_load_3d(sF, &tm_forcing, c0 + HS, r0, 0, bar, l2_policy(a.hint_forcing));
@@ -328,6 +393,28 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
     const bool edge = a.write_xhalo && (i == 0 || i == nx - 2);
     const long long colbase = idx(a.L, 0, HS, min(i, nx - 2) + HS);  // (v=0, interior row 0, pair)
     const unsigned long long pol_out = l2_policy(a.hint_out), pol_init = l2_policy(a.hint_init);
+    // Initial state of this thread's cell pair, pass by pass: 16-byte cp.async copies into a
+    // two-pass ring in shared memory, issued two passes ahead of their use (no registers held, no
+    // barrier needed: every thread reads back only what it copied itself).
+    auto fetch_init = [&](int p) {
+        const int kf = r0 + W * p + warp;
+        if (col_ok && kf < nz && !(p == NP - 1 && warp == W - 1)) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const double* src = a.init + colbase + v * a.L.vstride + (long long)kf * a.L.pitch;
+                const uint32_t dst = smem_u32(sIn + (((p & 1) * NVAR + v) * W + warp) * TC + col);
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+                             "l"(pol_init)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (HAS_INIT) {
+        fetch_init(NP - 1);
+        if (NP >= 2) fetch_init(NP - 2);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     mbar_wait(bar, 0);
 
     // set_bc_z folded in: tiles touching a wall rebuild the two halo rows in shared memory
@@ -357,15 +444,6 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
         const int lf = W * p + warp;  // tile-local interface row = tile-local cell row above it
         const int kf = r0 + lf;       // global interface index; bottom face of interior cell row kf
         const bool cell_ok = col_ok && kf < nz && !(p == NP - 1 && warp == W - 1);
-        Pair ini[4];
-        if (HAS_INIT && cell_ok) {  // initial state of the cell pair, in flight during the flux evaluation
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const double* src = a.init + colbase + v * a.L.vstride + (long long)kf * a.L.pitch;
-                asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
-                             : "=d"(ini[v].a), "=d"(ini[v].b) : "l"(src), "l"(pol_init));
-            }
-        }
         // taps: tile rows lf .. lf+3; A = left column of the pair, B = right column
         double a0[4], a1[4], a2[4], a3[4], b0[4], b1[4], b2[4], b3[4], fa[4], fb[4];
 #pragma unroll
@@ -394,6 +472,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
         for (int v = 0; v < 4; ++v)
             *reinterpret_cast<double2*>(xw + v * xstride) = make_double2(fa[v], fb[v]);
         __syncthreads();
+        if (HAS_INIT) asm volatile("cp.async.wait_group 1;" ::: "memory");  // this pass's initial state has landed
         if (cell_ok) {
             // flux through the top face: interface row lf+1 = warp w+1 of this pass, or warp 0 of the
             // pass above (p+1)
@@ -415,12 +494,20 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
                         ta += g.x; tb += g.y;
                     }
                 }
-                const double ia = HAS_INIT ? ini[v].a : a2[v];
-                const double ib = HAS_INIT ? ini[v].b : b2[v];
+                double ia = a2[v], ib = b2[v];
+                if (HAS_INIT) {
+                    const Pair in = lds2(sIn + (((p & 1) * NVAR + v) * W + warp) * TC + col);
+                    ia = in.a; ib = in.b;
+                }
                 store_pair(a, po, v * a.L.vstride, edge, i, fma(a.dt_stage, ta, ia), fma(a.dt_stage, tb, ib), pol_out);
             }
         }
+        if (HAS_INIT) {  // refill the ring slot just consumed with the pass two below (or an empty group)
+            if (p >= 2) fetch_init(p - 2);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     }
+    publish_tile(a, blockIdx.y * gridDim.x + blockIdx.x);
 }
 
 }  // namespace pmw
