@@ -102,6 +102,14 @@ struct pmw_ctx {
     bool chain_valid;
     int chain_tc, chain_tr, chain_ntx;
     int chain;  // tuning: 0 = always wait for the whole previous grid
+    // chunked sweeps: the three stages of a sweep only couple cells along the sweep direction, so
+    // bands of columns (z sweep) / rows (x sweep) run as independent kernel chains on their own
+    // streams and the tail of one kernel overlaps the head of the next band's kernel
+    int chunks;
+    cudaStream_t cstream[4];
+    cudaEvent_t ev_fork, ev_join[4];
+    cudaStream_t launch_stream;  // stream the stage launch helpers use
+    int cur_chunk, cur_nchunks;
     // bookkeeping
     long long launches;
     bool timing;
@@ -164,6 +172,13 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     for (int b = 0; b < 8; ++b) c->tile_flags[b] = nullptr;
     c->stage_epoch = 0;
     c->chain_valid = false;
+    // two bands per sweep measured best at 2048x1024 (tools/chunk_probe.py); small grids stay whole
+    c->chunks = ((long long)params->nx * params->nz >= (1ll << 20)) ? 2 : 1;
+    for (int k = 0; k < 4; ++k) { c->cstream[k] = nullptr; c->ev_join[k] = nullptr; }
+    c->ev_fork = nullptr;
+    c->launch_stream = nullptr;
+    c->cur_chunk = 0;
+    c->cur_nchunks = 1;
     c->chain = 0;  // measured slower than PDL alone on B200: a gpu-scope release per CTA costs more than the tail it hides
     c->peers = false;
     c->epoch = 0;
@@ -240,6 +255,11 @@ extern "C" int pmw_destroy(pmw_ctx* c)
     if (c->src_w) cudaFree(c->src_w);
     if (c->stats_partial) cudaFree(c->stats_partial);
     if (c->stats_out) cudaFree(c->stats_out);
+    for (int k = 0; k < 4; ++k) {
+        if (c->cstream[k]) { cudaStreamSynchronize(c->cstream[k]); cudaStreamDestroy(c->cstream[k]); }
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->flags) cudaFree(c->flags);
     if (c->edge_counters) cudaFree(c->edge_counters);
@@ -286,6 +306,9 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         c->l2_hints = value;
     } else if (!strcmp(key, "chain")) {
         c->chain = value ? 1 : 0;
+    } else if (!strcmp(key, "chunks")) {
+        NEED(value >= 1 && value <= 4, "chunks must be in 1..4");
+        c->chunks = value;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -300,6 +323,7 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     else if (!strcmp(key, "x_p")) *value = c->x_p;
     else if (!strcmp(key, "z_cfg")) *value = c->z_cfg;
     else if (!strcmp(key, "pdl")) *value = c->pdl;
+    else if (!strcmp(key, "chunks")) *value = c->chunks;
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
 }
@@ -518,10 +542,16 @@ static int set_smem(K kernel, size_t bytes)
 }
 
 template <int TR, int P>
-static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a)
+static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti, const StageArgs& a_in)
 {
     using T = XTile<TR, P>;
-    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + TR - 1) / TR + (a.push_epoch ? 1 : 0));
+    const int nty_all = (c->p.nz + TR - 1) / TR;
+    const int ty0 = (int)((long long)nty_all * c->cur_chunk / c->cur_nchunks);
+    const int ty1 = (int)((long long)nty_all * (c->cur_chunk + 1) / c->cur_nchunks);
+    StageArgs a = a_in;
+    a.tile_y0 = ty0;
+    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, ty1 - ty0 + (a.push_epoch ? 1 : 0));
+    if (ty1 == ty0) return PMW_OK;
     const size_t smem = T::smem_bytes(has_init);
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
 #define GO(HI, PM)                                                                   \
@@ -532,7 +562,7 @@ static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
             if (rc_ != PMW_OK) return rc_;                                           \
             attr_done |= 1ull << c->p.device;                                        \
         }                                                                            \
-        launch_ex(stage_x_tma<TR, P, HI, PM>, grid, dim3(T::THREADS), smem, c->stream, c->pdl && !c->timing, \
+        launch_ex(stage_x_tma<TR, P, HI, PM>, grid, dim3(T::THREADS), smem, c->launch_stream, c->pdl && !c->timing, \
                   tf, ti, a);                                                 \
     } while (0)
     if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
@@ -542,10 +572,16 @@ static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
 }
 
 template <int NP>
-static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const StageArgs& a)
+static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const StageArgs& a_in)
 {
     using T = ZTile<NP>;
-    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, (c->p.nz + T::TR - 1) / T::TR);
+    const int ntx_all = (c->p.nx + T::TC - 1) / T::TC;
+    const int tx0 = (int)((long long)ntx_all * c->cur_chunk / c->cur_nchunks);
+    const int tx1 = (int)((long long)ntx_all * (c->cur_chunk + 1) / c->cur_nchunks);
+    StageArgs a = a_in;
+    a.tile_x0 = tx0;
+    if (tx1 == tx0) return PMW_OK;
+    const dim3 grid(tx1 - tx0, (c->p.nz + T::TR - 1) / T::TR);
     const size_t smem = T::smem_bytes(has_init);
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
 #define GO(HI, PM)                                                                 \
@@ -556,7 +592,7 @@ static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
             if (rc_ != PMW_OK) return rc_;                                         \
             attr_done |= 1ull << c->p.device;                                      \
         }                                                                          \
-        launch_ex(stage_z_tma<NP, HI, PM>, grid, dim3(T::THREADS), smem, c->stream,  \
+        launch_ex(stage_z_tma<NP, HI, PM>, grid, dim3(T::THREADS), smem, c->launch_stream,  \
                   c->pdl && !c->timing, tf, a);                                    \
     } while (0)
     if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
@@ -601,6 +637,8 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.epoch_out = a.epoch_in = 0;
     a.prod_tc = a.prod_tr = a.prod_ntx = 1;
     a.chain_wrap = c->p.periodic_x;
+    a.tile_x0 = a.tile_y0 = 0;
+    if (c->cur_nchunks == 1) c->launch_stream = c->stream;
     a.dbg = c->peer_dbg;
     {   // l2_hints = decimal "abcd": a = forcing when init==forcing (stage 1), b = forcing otherwise,
         // c = init, d = out; each 0 normal | 1 evict_first | 2 evict_last
@@ -786,6 +824,55 @@ extern "C" int pmw_evolve_stage(pmw_ctx* c, int direction, int rk_stage, double 
     return rc;
 }
 
+// One directional sweep (three RK stages) as `chunks` independent kernel chains: bands of tile columns
+// for a z sweep, bands of tile rows for an x sweep.  Kernels are submitted stage-major
+// (A1 B1 A2 B2 A3 B3), each band on its own stream: B1 does not depend on A1, so it fills the SMs
+// while A1 drains, A2 (which waits for A1 through PDL) follows B1, and so on -- only the fork/join
+// at the sweep boundaries serialises.
+static int evolve_sweep_chunked(pmw_ctx* c, int direction, double dt)
+{
+    if (dt <= 0) dt = c->p.dt;
+    const int K = c->chunks;
+    if (!c->ev_fork) {
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        for (int k = 0; k < 4; ++k) {
+            CU_TRY(cudaStreamCreateWithFlags(&c->cstream[k], cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+        }
+    }
+    const int S = c->l2p[PMW_BUF_STATE], T0 = c->l2p[PMW_BUF_TMP], SP = c->spare;
+    if (direction == PMW_DIR_X && !c->xhalo_valid[S]) {
+        const int n = NVAR * c->p.nz;
+        bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[S], c->L);
+        LAUNCHED(c, "bc_x_kernel");
+        c->xhalo_valid[S] = true;
+    }
+    CU_TRY(cudaEventRecord(c->ev_fork, c->stream));
+    for (int k = 0; k < K; ++k) CU_TRY(cudaStreamWaitEvent(c->cstream[k], c->ev_fork, 0));
+    int rc = PMW_OK;
+    c->cur_nchunks = K;
+    for (int rk = 1; rk <= 3 && rc == PMW_OK; ++rk) {
+        for (int k = 0; k < K && rc == PMW_OK; ++k) {
+            c->cur_chunk = k;
+            c->launch_stream = c->cstream[k];
+            if (rk == 1) rc = launch_stage(c, direction, S, S, T0, dt / 3, true, true);
+            else if (rk == 2) rc = launch_stage(c, direction, S, T0, SP, dt / 2, true, true);
+            else rc = launch_stage(c, direction, S, SP, S, dt / 1, true, true);
+        }
+    }
+    c->cur_chunk = 0;
+    c->cur_nchunks = 1;
+    c->launch_stream = c->stream;
+    if (rc != PMW_OK) return rc;
+    c->l2p[PMW_BUF_TMP] = SP;
+    c->spare = T0;
+    for (int k = 0; k < K; ++k) {
+        CU_TRY(cudaEventRecord(c->ev_join[k], c->cstream[k]));
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+    }
+    return PMW_OK;
+}
+
 extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
 {
     BIND(c);
@@ -793,13 +880,19 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
     NEED(c->p.periodic_x || c->peers,
          "pmw_evolve: a slab context (periodic_x=0) needs pmw_connect_peers, or must be stepped stage by "
          "stage with pmw_evolve_stage and a halo exchange before every x stage");
+    // (x sweeps of a connected slab carry the halo push / epoch wait per stage: those stay whole)
+    const bool chunk_ok = c->chunks > 1 && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && !c->timing;
     for (int n = 0; n < nsteps; ++n) {
         const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
-        for (int d = 0; d < 2; ++d)
-            for (int s = 1; s <= 3; ++s) {
-                int rc = pmw_evolve_stage(c, dirs[d], s, dt);
-                if (rc != PMW_OK) return rc;
+        for (int d = 0; d < 2; ++d) {
+            int rc = PMW_OK;
+            if (chunk_ok && (!c->peers || dirs[d] == PMW_DIR_Z)) {
+                rc = evolve_sweep_chunked(c, dirs[d], dt);
+            } else {
+                for (int s = 1; s <= 3 && rc == PMW_OK; ++s) rc = pmw_evolve_stage(c, dirs[d], s, dt);
             }
+            if (rc != PMW_OK) return rc;
+        }
         c->reverse = !c->reverse;
     }
     return PMW_OK;

@@ -95,6 +95,9 @@ struct StageArgs {
     unsigned int epoch_out, epoch_in;
     int prod_tc, prod_tr, prod_ntx;  // producer tile size in cells (x, z) and tiles per row
     int chain_wrap;                  // periodic domain: halo columns are images stored by the edge tiles
+    // Chunked sweeps: this launch covers only the tile columns (z stages) / tile rows (x stages)
+    // starting at these offsets; the grid dimensions give the extent.
+    int tile_x0, tile_y0;
 };
 
 __device__ __forceinline__ unsigned long long l2_policy(int kind)

@@ -235,6 +235,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
         ty = lin % nty;
         tx = (cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1);
     }
+    ty += a.tile_y0;            // chunked sweeps: this launch covers a band of tile rows
     const int c0 = tx * T::TC;  // first interior column of the tile (even)
     const int r0 = ty * TR;     // first interior row
     pdl_launch_dependents();
@@ -358,7 +359,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sIn + (HAS_INIT ? T::I_ELEMS : 0));
 
     const int nz = a.L.nz, nx = a.L.nx;
-    const int c0 = blockIdx.x * TC;
+    const int c0 = (blockIdx.x + a.tile_x0) * TC;  // chunked sweeps: a band of tile columns per launch
     const int r0 = blockIdx.y * T::TR;
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
@@ -507,7 +508,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
             else asm volatile("cp.async.commit_group;" ::: "memory");
         }
     }
-    publish_tile(a, blockIdx.y * gridDim.x + blockIdx.x);
+    publish_tile(a, blockIdx.y * ((nx + TC - 1) / TC) + blockIdx.x + a.tile_x0);
 }
 
 }  // namespace pmw
