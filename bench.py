@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cell-updates/sec (fp64, per RK3 step)"
 UNIT = "cell-updates/s"
-NX_SLAB, NZ = 2048, 1024
+NX_SLAB, NZ = 2048, 1024  # BASELINE config 2 (per-GPU slab); --nx/--nz override it for the size studies
 BYTES_PER_CELL_STEP = 512.0  # 2 sweeps x (64 + 96 + 96) B: SURVEY.md section 8d / DESIGN.md
 STAGES_PER_STEP = 6
 
@@ -363,12 +363,12 @@ def run_gpu(args, rank, local_rank, world):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"thermal rising bubble, nx={NX_SLAB * world} nz={NZ} fp64"
-                               + (" (BASELINE config 2)" if world == 1 else
+                               + ((" (BASELINE config 2)" if (NX_SLAB, NZ) == (2048, 1024) else "") if world == 1 else
                                   f" = {world} x-slabs of {NX_SLAB}x{NZ}, ring halo exchange per x stage ({args.halo})"),
                    "nx": NX_SLAB * world, "nz": NZ, "variant": args.variant, "pow_mode": args.pow_mode,
                    "tiles": {k: solver.get_tuning(k) for k in ("x_tr", "x_p", "z_cfg")},
-                   "l2": "no flush: working set = 3 state buffers x 67.5 MB = 202 MB per GPU > 126 MB L2 "
-                         "(inputs larger than L2)",
+                   "l2": f"no flush: working set = 3 state buffers x {4 * (NZ + 4) * (NX_SLAB + 4) * 8 / 1e6:.1f} MB "
+                         "per GPU > 126 MB L2 (inputs larger than L2)",
                    "state_finite_after_run": finite,
                    "mass_rel_change": (m1 - m0) / m0, "energy_rel_change": (e1 - e0) / e0},
         "clocks": clocks,
@@ -403,11 +403,18 @@ def main():
     ap.add_argument("--tune", action="append", help="key=value tile tuning (x_tr, x_p, z_cfg)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="slab halo exchange at N>1: peer-memory stores from the stage kernels, or NCCL send/recv")
+    ap.add_argument("--nx", type=int, default=None, help="per-GPU slab width (default 2048 = BASELINE config 2)")
+    ap.add_argument("--nz", type=int, default=None, help="grid height (default 1024)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline work")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global NX_SLAB, NZ
+    if args.nx:
+        NX_SLAB = args.nx
+    if args.nz:
+        NZ = args.nz
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -179,9 +179,7 @@ int pmw_peer_status(pmw_ctx *ctx, int *timed_out);
  * (0|1: programmatic dependent launch between consecutive stage kernels; default 1), "l2_hints"
  * (decimal abcd = L2 eviction priority of: forcing in stage 1, forcing in stages 2-3, init, out;
  * 0 normal, 1 evict_first, 2 evict_last; default 1100), "chunks" (1..4 independent bands per directional sweep, each a kernel chain on
- * its own stream so that kernel tails overlap; default 2 for grids of >= 2^20 cells), "chain" (0|1, default 0: experimental
- * tile-level dependency flags between consecutive stages instead of whole-grid waits -- measured
- * slower than PDL alone, kept for study), "peer_dbg" (development switches). */
+ * its own stream so that kernel tails overlap; default 2 for grids of >= 2^20 cells), "peer_dbg" (development switches). */
 int pmw_set_tuning(pmw_ctx *ctx, const char *key, int value);
 int pmw_get_tuning(pmw_ctx *ctx, const char *key, int *value);
 

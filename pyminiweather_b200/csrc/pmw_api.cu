@@ -95,13 +95,6 @@ struct pmw_ctx {
     unsigned int* edge_counters;     // last-arriver counter of the push CTAs
     unsigned long long epoch;        // number of x stages run since pmw_connect_peers
     std::vector<void*> ipc_opened;
-    // tile-level chaining of consecutive fused stage kernels
-    unsigned int* tile_flags[8];  // ring over stages: a word is rewritten 8 stages later at the earliest
-    size_t tile_flags_len;
-    unsigned int stage_epoch;
-    bool chain_valid;
-    int chain_tc, chain_tr, chain_ntx;
-    int chain;  // tuning: 0 = always wait for the whole previous grid
     // chunked sweeps: the three stages of a sweep only couple cells along the sweep direction, so
     // bands of columns (z sweep) / rows (x sweep) run as independent kernel chains on their own
     // streams and the tail of one kernel overlaps the head of the next band's kernel
@@ -169,9 +162,6 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->stats_partial = c->stats_out = nullptr;
     c->flags = nullptr;
     c->edge_counters = nullptr;
-    for (int b = 0; b < 8; ++b) c->tile_flags[b] = nullptr;
-    c->stage_epoch = 0;
-    c->chain_valid = false;
     // two bands per sweep measured best at 2048x1024 (tools/chunk_probe.py); small grids stay whole
     c->chunks = ((long long)params->nx * params->nz >= (1ll << 20)) ? 2 : 1;
     for (int k = 0; k < 4; ++k) { c->cstream[k] = nullptr; c->ev_join[k] = nullptr; }
@@ -179,7 +169,6 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->launch_stream = nullptr;
     c->cur_chunk = 0;
     c->cur_nchunks = 1;
-    c->chain = 0;  // measured slower than PDL alone on B200: a gpu-scope release per CTA costs more than the tail it hides
     c->peers = false;
     c->epoch = 0;
     for (int b = 0; b < 3; ++b) {
@@ -218,14 +207,6 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
             cudaMalloc(&c->flags, 4 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(c->flags, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&c->edge_counters, 2 * sizeof(unsigned int)) != cudaSuccess ||
-            [&]() {  // one completion word per tile of the finest tiling either stage kernel can use
-                c->tile_flags_len = (size_t)((params->nx + 61) / 62 + 1) * ((params->nz + 2) / 3 + 1);
-                for (int b = 0; b < 8; ++b)
-                    if (cudaMalloc(&c->tile_flags[b], c->tile_flags_len * sizeof(unsigned int)) != cudaSuccess ||
-                        cudaMemset(c->tile_flags[b], 0, c->tile_flags_len * sizeof(unsigned int)) != cudaSuccess)
-                        return true;
-                return false;
-            }() ||
             cudaMemset(c->edge_counters, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
             pmw_destroy(c);
             return fail(PMW_ECUDA, "cudaMalloc of auxiliary buffers failed");
@@ -263,8 +244,6 @@ extern "C" int pmw_destroy(pmw_ctx* c)
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->flags) cudaFree(c->flags);
     if (c->edge_counters) cudaFree(c->edge_counters);
-    for (int b = 0; b < 8; ++b)
-        if (c->tile_flags[b]) cudaFree(c->tile_flags[b]);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     delete c;
     return PMW_OK;
@@ -287,7 +266,6 @@ extern "C" int pmw_synchronize(pmw_ctx* c)
 extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
 {
     BIND(c);
-    c->chain_valid = false;
     NEED(key, "pmw_set_tuning: null key");
     if (!strcmp(key, "x_tr")) {
         NEED(value == 4 || value == 8, "x_tr must be 4 or 8");
@@ -304,8 +282,6 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         c->peer_dbg = value;
     } else if (!strcmp(key, "l2_hints")) {
         c->l2_hints = value;
-    } else if (!strcmp(key, "chain")) {
-        c->chain = value ? 1 : 0;
     } else if (!strcmp(key, "chunks")) {
         NEED(value >= 1 && value <= 4, "chunks must be in 1..4");
         c->chunks = value;
@@ -412,7 +388,6 @@ static int copy_state(pmw_ctx* c, int buf, double* host, bool to_device, bool sy
     const size_t NX = c->p.nx + 4, rows = (size_t)NVAR * (c->p.nz + 4);
     double* dev = c->base[c->l2p[buf]];
     if (to_device) {
-        c->chain_valid = false;
         CU_TRY(cudaMemcpy2DAsync(dev, c->L.pitch * sizeof(double), host, NX * sizeof(double), NX * sizeof(double),
                                  rows, cudaMemcpyHostToDevice, c->stream));
         c->xhalo_valid[c->l2p[buf]] = false;
@@ -469,7 +444,6 @@ static int after_launch(pmw_ctx* c, const char* what)
 extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
 {
     BIND(c);
-    c->chain_valid = false;
     CHECK_BUF(buf);
     const int n = NVAR * c->p.nz;
     bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L);
@@ -481,7 +455,6 @@ extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
 extern "C" int pmw_bc_z(pmw_ctx* c, int buf)
 {
     BIND(c);
-    c->chain_valid = false;
     CHECK_BUF(buf);
     NEED(c->hydro_set, "pmw_bc_z: hydrostatic profiles not set");
     const int n = c->p.nx + 4;
@@ -571,6 +544,66 @@ static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
     return PMW_OK;
 }
 
+// Gravity-wave configuration: the HAS_SRC instantiations exist for the default tile shapes only.
+static int launch_x_tma_src(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const CUtensorMap& ti,
+                            const StageArgs& a_in)
+{
+    using T = XTile<4, 2>;
+    const int nty_all = (c->p.nz + 3) / 4;
+    const int ty0 = (int)((long long)nty_all * c->cur_chunk / c->cur_nchunks);
+    const int ty1 = (int)((long long)nty_all * (c->cur_chunk + 1) / c->cur_nchunks);
+    StageArgs a = a_in;
+    a.tile_y0 = ty0;
+    const dim3 grid((c->p.nx + T::TC - 1) / T::TC, ty1 - ty0 + (a.push_epoch ? 1 : 0));
+    if (ty1 == ty0) return PMW_OK;
+    const size_t smem = T::smem_bytes(has_init);
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+#define GO(HI, PM)                                                                             \
+    do {                                                                                       \
+        static unsigned long long attr_done = 0;                                               \
+        if (!(attr_done >> c->p.device & 1ull)) {                                              \
+            int rc_ = set_smem(stage_x_tma<4, 2, HI, PM, true>, T::smem_bytes(true));          \
+            if (rc_ != PMW_OK) return rc_;                                                     \
+            attr_done |= 1ull << c->p.device;                                                  \
+        }                                                                                      \
+        launch_ex(stage_x_tma<4, 2, HI, PM, true>, grid, dim3(T::THREADS), smem, c->launch_stream, \
+                  c->pdl && !c->timing, tf, ti, a);                                            \
+    } while (0)
+    if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
+    else          { if (fast) GO(false, 1); else GO(false, 0); }
+#undef GO
+    return PMW_OK;
+}
+
+static int launch_z_tma_src(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const StageArgs& a_in)
+{
+    using T = ZTile<3>;
+    const int ntx_all = (c->p.nx + T::TC - 1) / T::TC;
+    const int tx0 = (int)((long long)ntx_all * c->cur_chunk / c->cur_nchunks);
+    const int tx1 = (int)((long long)ntx_all * (c->cur_chunk + 1) / c->cur_nchunks);
+    StageArgs a = a_in;
+    a.tile_x0 = tx0;
+    if (tx1 == tx0) return PMW_OK;
+    const dim3 grid(tx1 - tx0, (c->p.nz + T::TR - 1) / T::TR);
+    const size_t smem = T::smem_bytes(has_init);
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+#define GO(HI, PM)                                                                         \
+    do {                                                                                   \
+        static unsigned long long attr_done = 0;                                           \
+        if (!(attr_done >> c->p.device & 1ull)) {                                          \
+            int rc_ = set_smem(stage_z_tma<3, HI, PM, true>, T::smem_bytes(true));         \
+            if (rc_ != PMW_OK) return rc_;                                                 \
+            attr_done |= 1ull << c->p.device;                                              \
+        }                                                                                  \
+        launch_ex(stage_z_tma<3, HI, PM, true>, grid, dim3(T::THREADS), smem, c->launch_stream, \
+                  c->pdl && !c->timing, tf, a);                                            \
+    } while (0)
+    if (has_init) { if (fast) GO(true, 1); else GO(true, 0); }
+    else          { if (fast) GO(false, 1); else GO(false, 0); }
+#undef GO
+    return PMW_OK;
+}
+
 template <int NP>
 static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const StageArgs& a_in)
 {
@@ -632,11 +665,6 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.nbr_forcing_left = a.nbr_forcing_right = nullptr;
     a.nbr_flags_left = a.nbr_flags_right = nullptr;
     a.push_counter = c->edge_counters;
-    a.tile_flags_out = nullptr;
-    a.prod_flags = nullptr;
-    a.epoch_out = a.epoch_in = 0;
-    a.prod_tc = a.prod_tr = a.prod_ntx = 1;
-    a.chain_wrap = c->p.periodic_x;
     a.tile_x0 = a.tile_y0 = 0;
     if (c->cur_nchunks == 1) c->launch_stream = c->stream;
     a.dbg = c->peer_dbg;
@@ -685,7 +713,6 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     }
 
     if (c->p.variant == PMW_VARIANT_DIRECT || (c->p.nx & 1)) {  // the TMA kernels pair cells in x
-        c->chain_valid = false;
         const dim3 block(64, 4);
         const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4 + (direction == PMW_DIR_X ? push_rows : 0));
         const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
@@ -699,25 +726,18 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     } else {
         const CUtensorMap *tf = nullptr, *ti = nullptr;
         int rc;
-        // tile-level chaining with the previous fused stage kernel
-        const int my_tc = (direction == PMW_DIR_X) ? 64 * c->x_p - 2 : 64;
-        const int my_tr = (direction == PMW_DIR_X) ? c->x_tr : 4 * c->z_cfg - 1;
-        const int my_ntx = (c->p.nx + my_tc - 1) / my_tc;
-        const unsigned int e = ++c->stage_epoch;
-        a.tile_flags_out = c->chain ? c->tile_flags[e % 8] : nullptr;
-        a.epoch_out = e;
-        if (c->chain && c->chain_valid && fuse_bc_z) {
-            a.prod_flags = c->tile_flags[(e - 1) % 8];
-            a.epoch_in = e - 1;
-            a.prod_tc = c->chain_tc;
-            a.prod_tr = c->chain_tr;
-            a.prod_ntx = c->chain_ntx;
-        }
-        c->chain_valid = fuse_bc_z && c->chain;
-        c->chain_tc = my_tc;
-        c->chain_tr = my_tr;
-        c->chain_ntx = my_ntx;
-        if (direction == PMW_DIR_X) {
+        if (c->src_w) {
+            // gravity-wave forcing: kernels instantiated with HAS_SRC, default tile shapes only
+            if (direction == PMW_DIR_X) {
+                if ((rc = get_tmap(c, p_forcing, 132, 4, &tf)) != PMW_OK) return rc;
+                if ((rc = get_tmap(c, p_init, 128, 4, &ti)) != PMW_OK) return rc;
+                rc = launch_x_tma_src(c, has_init, *tf, *ti, a);
+            } else {
+                if ((rc = get_tmap(c, p_forcing, 64, 15, &tf)) != PMW_OK) return rc;
+                rc = launch_z_tma_src(c, has_init, *tf, a);
+            }
+            if (rc != PMW_OK) return rc;
+        } else if (direction == PMW_DIR_X) {
             const int fw = 64 * c->x_p + 4, iw = 64 * c->x_p;
             if ((rc = get_tmap(c, p_forcing, fw, c->x_tr, &tf)) != PMW_OK) return rc;
             if ((rc = get_tmap(c, p_init, iw, c->x_tr, &ti)) != PMW_OK) return rc;
@@ -979,7 +999,6 @@ extern "C" int pmw_pack_halo_x(pmw_ctx* c, int buf, double* to_left, double* to_
 extern "C" int pmw_unpack_halo_x(pmw_ctx* c, int buf, const double* from_left, const double* from_right)
 {
     BIND(c);
-    c->chain_valid = false;
     CHECK_BUF(buf);
     NEED(from_left && from_right, "pmw_unpack_halo_x: null message buffer");
     const int n = NVAR * c->p.nz * 2;
@@ -1058,7 +1077,6 @@ extern "C" int pmw_local_ptrs(pmw_ctx* c, void* ptrs_out[4])
 extern "C" int pmw_connect_peers(pmw_ctx* c, void* const left[4], void* const right[4])
 {
     BIND(c);
-    c->chain_valid = false;
     NEED(!c->p.periodic_x, "pmw_connect_peers: the context was created with periodic_x=1");
     NEED((c->p.nx & 1) == 0, "pmw_connect_peers: the slab width must be even");
     NEED(left && right, "pmw_connect_peers: null argument");

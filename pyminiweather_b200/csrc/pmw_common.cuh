@@ -62,7 +62,8 @@ struct StageArgs {
     double* out_left;   // same logical buffer on the left  slab neighbour (== out when periodic_x)
     double* out_right;  // same logical buffer on the right slab neighbour
     Hydro hy;
-    const double* src_w;  // [nz][nx] extra rho*w tendency (ic_type "gravity", source.py:43-50) or nullptr
+    const double* src_w;  // [nz][nx] extra rho*w tendency (ic_type "gravity", source.py:43-50) or nullptr;
+                          // the TMA kernels read it only in their HAS_SRC instantiations
     double hv_coeff;  // -hv_beta*d/(16*dt_full)   (interpolate.py:101,149)
     double inv_d;     // 1/dx or 1/dz
     double dt_stage;
@@ -86,15 +87,6 @@ struct StageArgs {
     int dbg;  // development switches (pmw_set_tuning "peer_dbg"); 0 in production
     // L2 eviction priority per operand: 0 normal, 1 evict_first, 2 evict_last (createpolicy)
     int hint_forcing, hint_init, hint_out;
-    // Tile-level chaining of consecutive stage kernels (see wait_producer_tiles): every CTA publishes
-    // tile_flags_out[tile] = epoch_out when its stores are done; when prod_flags != nullptr a CTA
-    // waits only for the producer tiles its own tile depends on instead of for the whole previous
-    // grid (griddepcontrol.wait), so the head of stage n+1 overlaps the tail of stage n.
-    unsigned int* tile_flags_out;
-    const unsigned int* prod_flags;
-    unsigned int epoch_out, epoch_in;
-    int prod_tc, prod_tr, prod_ntx;  // producer tile size in cells (x, z) and tiles per row
-    int chain_wrap;                  // periodic domain: halo columns are images stored by the edge tiles
     // Chunked sweeps: this launch covers only the tile columns (z stages) / tile rows (x stages)
     // starting at these offsets; the grid dimensions give the extent.
     int tile_x0, tile_y0;

@@ -102,52 +102,6 @@ __device__ __forceinline__ void wait_epoch(unsigned long long* flags, int which,
     asm volatile("fence.proxy.async;" ::: "memory");  // order the acquire before the TMA (async proxy) reads
 }
 
-// Tile-level dependency wait (one thread per CTA).  The tile covering cells [c_lo, c_hi] x
-// [r_lo, r_hi] of the consumer stage may start once every producer-stage tile that
-//   - wrote a cell this tile reads (its own cells plus the 2-cell stencil halo), or
-//   - read a cell this tile overwrites (the producer's stencil halo)
-// has published its epoch.  Both conditions are covered by waiting for the producer tiles that
-// intersect the tile grown by 2 cells on every side; in a periodic domain columns beyond the edge
-// are images stored by the producer tiles that own the opposite edge.
-__device__ __forceinline__ void poll_tile(const StageArgs& a, int ptx, int pty)
-{
-    const unsigned int* f = a.prod_flags + (long long)pty * a.prod_ntx + ptx;
-    const long long t0 = clock64();
-    unsigned int v;
-    do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        if ((int)(v - a.epoch_in) >= 0) break;
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s watchdog: flag an error instead of hanging
-            a.flags[2] = 2ull;
-            break;
-        }
-    } while (true);
-}
-__device__ __forceinline__ void wait_producer_tiles(const StageArgs& a, int c_lo, int c_hi, int r_lo, int r_hi)
-{
-    const int nx = a.L.nx, nz = a.L.nz;
-    c_lo -= 2; c_hi += 2; r_lo -= 2; r_hi += 2;
-    const int ty0 = max(r_lo, 0) / a.prod_tr, ty1 = min(r_hi, nz - 1) / a.prod_tr;
-    const int tx0 = max(c_lo, 0) / a.prod_tc, tx1 = min(c_hi, nx - 1) / a.prod_tc;
-    for (int pty = ty0; pty <= ty1; ++pty) {
-        for (int ptx = tx0; ptx <= tx1; ++ptx) poll_tile(a, ptx, pty);
-        if (a.chain_wrap) {
-            if (c_lo < 0) poll_tile(a, (nx - 1) / a.prod_tc, pty);
-            if (c_hi > nx - 1) poll_tile(a, 0, pty);
-        }
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");  // acquire (generic proxy) before the TMA reads
-}
-// Publish this tile's completion: all stores of the CTA are ordered before the flag by the barrier
-// plus a gpu-scope release by one thread (the CUTLASS semaphore pattern).
-__device__ __forceinline__ void publish_tile(const StageArgs& a, int tile_id)
-{
-    if (!a.tile_flags_out) return;  // chaining off (the default: see pmw_set_tuning "chain")
-    __syncthreads();
-    if (threadIdx.x == 0)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.tile_flags_out + tile_id), "r"(a.epoch_out) : "memory");
-}
-
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -171,8 +125,8 @@ __device__ __forceinline__ Pair lds2(const double* p)  // p is 16-byte aligned s
 __device__ __forceinline__ void store_pair(const StageArgs& a, double* po, long long voff, bool edge, int i,
                                            double x, double y, unsigned long long policy)
 {
-    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(po + voff), "d"(x), "d"(y), "l"(policy)
-                 : "memory");
+    (void)policy;  // an eviction hint on the stores never helped (tools/l2_probe.py) and costs two registers
+    *reinterpret_cast<double2*>(po + voff) = make_double2(x, y);
     if (edge) {
         const long long o = (po - a.out) + voff;
         if (i == 0) *reinterpret_cast<double2*>(a.out_left + o + a.L.nx) = make_double2(x, y);
@@ -201,8 +155,8 @@ struct XTile {
     }
 };
 
-template <int TR, int P, bool HAS_INIT, int POW_MODE>
-__global__ void __launch_bounds__(32 * TR)
+template <int TR, int P, bool HAS_INIT, int POW_MODE, bool HAS_SRC = false>
+__global__ void __launch_bounds__(32 * TR, (TR == 4 && !HAS_SRC) ? 5 : 1)  // 4-warp tiles: 5 CTAs/SM (<= 96 registers)
 stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constant__ CUtensorMap tm_init,
             const StageArgs a)
 {
@@ -245,13 +199,8 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
         mbar_init(bar, 1);
     }
     __syncthreads();
-    // Everything below reads or overwrites state produced by the previous stage: wait for the whole
-    // previous grid, or -- chained -- only for the producer tiles this tile depends on (thread 0 is
-    // the only thread that touches global memory before the mbarrier wait).
-    if (!a.prod_flags) pdl_wait();
+    pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
-        if (a.prod_flags)
-            wait_producer_tiles(a, c0, min(c0 + T::TC, a.L.nx) - 1, r0, min(r0 + TR, a.L.nz) - 1);
         if (a.wait_epoch && !(a.dbg & 2)) {
             if (tx == 0) wait_epoch(a.flags, 0, a.wait_epoch);
             if (tx == ntx - 1) wait_epoch(a.flags, 1, a.wait_epoch);
@@ -303,7 +252,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
                     ia = t2[v]; ib = t3[v];
                 }
                 double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
-                if (v == WMOM && a.src_w) {  // gravity-wave forcing (source.py:43-50)
+                if (HAS_SRC && v == WMOM) {  // gravity-wave forcing (source.py:43-50)
                     const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)k * nx + i));
                     ta += g.x; tb += g.y;
                 }
@@ -313,7 +262,6 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
             }
         }
     }
-    publish_tile(a, ty * ntx + tx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -345,7 +293,7 @@ struct ZTile {
     }
 };
 
-template <int NP, bool HAS_INIT, int POW_MODE>
+template <int NP, bool HAS_INIT, int POW_MODE, bool HAS_SRC = false>
 __global__ void __launch_bounds__(128, HAS_INIT ? 4 : 5)
 stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
 {
@@ -374,15 +322,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
         sH[3 * W * NP + threadIdx.x] = __ldg(a.hy.pressure_int + kc);
     }
     __syncthreads();
-    // wait for the previous stage: the whole grid, or (chained) the producer tiles of this tile; all
-    // threads read `init` below, so the chained wait is followed by a block barrier
-    if (!a.prod_flags) {
-        pdl_wait();
-    } else {
-        if (threadIdx.x == 0)
-            wait_producer_tiles(a, c0, min(c0 + TC, nx) - 1, r0, min(r0 + T::TR, nz) - 1);
-        __syncthreads();
-    }
+    pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar, (uint32_t)(T::F_ELEMS * sizeof(double)));
         tma_load_3d(sF, &tm_forcing, c0 + HS, r0, 0, bar, l2_policy(a.hint_forcing));
@@ -490,7 +430,7 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
                 if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250); cell kf is tap 2
                     ta = fma(-a2[DENS], GRAV, ta);
                     tb = fma(-b2[DENS], GRAV, tb);
-                    if (a.src_w) {  // gravity-wave forcing (source.py:43-50)
+                    if (HAS_SRC) {  // gravity-wave forcing (source.py:43-50)
                         const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)kf * nx + i));
                         ta += g.x; tb += g.y;
                     }
@@ -508,7 +448,6 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
             else asm volatile("cp.async.commit_group;" ::: "memory");
         }
     }
-    publish_tile(a, blockIdx.y * ((nx + TC - 1) / TC) + blockIdx.x + a.tile_x0);
 }
 
 }  // namespace pmw

@@ -43,6 +43,8 @@ def mk(variant="tma"):
 s = mk("direct")
 report("direct x", bench(s, 1)); report("direct z", bench(s, 2)); s.close()
 s = mk()
+extra = dict(kv.split("=") for kv in sys.argv[3:])
+if extra: s.set_tuning(**{k: int(v) for k, v in extra.items()})
 for tr, xp in itertools.product((4, 8), (1, 2, 3)):
     s.set_tuning(x_tr=tr, x_p=xp)
     report(f"x tr={tr} p={xp}", bench(s, 1))
