@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include "pmw_aux.cuh"
 #include "pmw_direct.cuh"
 #include "pmw_tma.cuh"
+#include "pmw_sweep.cuh"
 #include "pmw_unfused.cuh"
 
 using namespace pmw;
@@ -71,6 +73,9 @@ struct pmw_ctx {
     int l2p[2];  // logical (STATE, TMP) -> physical buffer
     int spare;
     bool xhalo_valid[3];  // x halo columns hold the periodic image of the interior
+    bool xhalo6_valid[3];  // ... and so do the four further columns a fused x sweep reads (6-wide image)
+    // fused sweeps (pmw_sweep.cuh): 1 = pmw_evolve runs one kernel per directional sweep
+    int fuse, keep_tmp, sweep_lz, sweep_xp;
     double* hydro_blob;
     double* src_w;  // gravity-wave forcing field or nullptr
     Hydro hy;
@@ -153,7 +158,8 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->p = *params;
     c->L.nx = params->nx;
     c->L.nz = params->nz;
-    c->L.pitch = round_up(LPAD + params->nx + 2 * HS, 16);
+    // room for the 6-wide x halo of the fused sweeps: array columns -4 .. nx+7
+    c->L.pitch = round_up(LPAD + params->nx + HS + SWEEP_HALO, 16);
     c->L.vstride = (long long)c->L.pitch * (params->nz + 2 * HS);
     c->buf_doubles = (size_t)NVAR * c->L.vstride + 32;
     for (int b = 0; b < 3; ++b) c->alloc[b] = nullptr;
@@ -181,7 +187,12 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
         cudaMemset(c->alloc[b], 0, c->buf_doubles * sizeof(double));
         c->base[b] = c->alloc[b] + LPAD;
         c->xhalo_valid[b] = false;
+        c->xhalo6_valid[b] = false;
     }
+    c->fuse = 1;
+    c->keep_tmp = 1;
+    c->sweep_lz = 0;  // 0 = choose from the grid (pick_sweep_lz)
+    c->sweep_xp = 2;
     c->l2p[PMW_BUF_STATE] = 0;
     c->l2p[PMW_BUF_TMP] = 1;
     c->spare = 2;
@@ -285,6 +296,16 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
     } else if (!strcmp(key, "chunks")) {
         NEED(value >= 1 && value <= 4, "chunks must be in 1..4");
         c->chunks = value;
+    } else if (!strcmp(key, "fuse")) {
+        c->fuse = value ? 1 : 0;
+    } else if (!strcmp(key, "keep_tmp")) {
+        c->keep_tmp = value ? 1 : 0;
+    } else if (!strcmp(key, "sweep_lz")) {
+        NEED(value == 0 || value >= 8, "sweep_lz must be 0 (automatic) or >= 8");
+        c->sweep_lz = value;
+    } else if (!strcmp(key, "sweep_xp")) {
+        NEED(value == 2 || value == 3, "sweep_xp must be 2 or 3");
+        c->sweep_xp = value;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -300,6 +321,10 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     else if (!strcmp(key, "z_cfg")) *value = c->z_cfg;
     else if (!strcmp(key, "pdl")) *value = c->pdl;
     else if (!strcmp(key, "chunks")) *value = c->chunks;
+    else if (!strcmp(key, "fuse")) *value = c->fuse;
+    else if (!strcmp(key, "keep_tmp")) *value = c->keep_tmp;
+    else if (!strcmp(key, "sweep_lz")) *value = c->sweep_lz;
+    else if (!strcmp(key, "sweep_xp")) *value = c->sweep_xp;
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
 }
@@ -391,6 +416,7 @@ static int copy_state(pmw_ctx* c, int buf, double* host, bool to_device, bool sy
         CU_TRY(cudaMemcpy2DAsync(dev, c->L.pitch * sizeof(double), host, NX * sizeof(double), NX * sizeof(double),
                                  rows, cudaMemcpyHostToDevice, c->stream));
         c->xhalo_valid[c->l2p[buf]] = false;
+        c->xhalo6_valid[c->l2p[buf]] = false;
     } else {
         CU_TRY(cudaMemcpy2DAsync(host, NX * sizeof(double), dev, c->L.pitch * sizeof(double), NX * sizeof(double),
                                  rows, cudaMemcpyDeviceToHost, c->stream));
@@ -449,6 +475,7 @@ extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
     bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L);
     LAUNCHED(c, "bc_x_kernel");
     c->xhalo_valid[c->l2p[buf]] = true;
+    c->xhalo6_valid[c->l2p[buf]] = false;
     return PMW_OK;
 }
 
@@ -463,22 +490,28 @@ extern "C" int pmw_bc_z(pmw_ctx* c, int buf)
     return PMW_OK;
 }
 
-static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** out)
+// wide = false: the reference-shaped array [4][nz+4][nx+4] (map column 0 = array column 0);
+// wide = true : the same rows with the 6-wide x halo of the fused sweeps, [4][nz+4][nx+12]
+//               (map column 0 = array column -4 = interior column -6).
+static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** out, bool wide = false)
 {
+    const int key_buf = pbuf + (wide ? 16 : 0);
     for (const TmapKey& k : c->tmaps)
-        if (k.buf == pbuf && k.bw == bw && k.bh == bh) {
+        if (k.buf == key_buf && k.bw == bw && k.bh == bh) {
             *out = &k.map;
             return PMW_OK;
         }
     if (c->tmaps.capacity() < 256) c->tmaps.reserve(256);  // keep returned pointers stable
     if (c->tmaps.size() >= 256) c->tmaps.clear();           // tuning sweeps: start over
     TmapKey k;
-    k.buf = pbuf; k.bw = bw; k.bh = bh;
-    const cuuint64_t gdim[3] = {(cuuint64_t)(c->p.nx + 4), (cuuint64_t)(c->p.nz + 4), (cuuint64_t)NVAR};
+    k.buf = key_buf; k.bw = bw; k.bh = bh;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(c->p.nx + (wide ? 2 * SWEEP_HALO : 2 * HS)), (cuuint64_t)(c->p.nz + 4),
+                                (cuuint64_t)NVAR};
     const cuuint64_t gstride[2] = {(cuuint64_t)c->L.pitch * sizeof(double), (cuuint64_t)c->L.vstride * sizeof(double)};
     const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)NVAR};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = c->encode(&k.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->base[pbuf], gdim, gstride, box, estr,
+    CUresult r = c->encode(&k.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                           c->base[pbuf] - (wide ? SWEEP_HALO - HS : 0), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -763,6 +796,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     LAUNCHED(c, direction == PMW_DIR_X ? "x stage kernel" : "z stage kernel");
     if (c->timing) CU_TRY(cudaEventRecord(e1, c->stream));
     c->xhalo_valid[p_out] = a.write_xhalo != 0;
+    c->xhalo6_valid[p_out] = false;
     return PMW_OK;
 }
 
@@ -784,7 +818,8 @@ extern "C" int pmw_stage(pmw_ctx* c, int direction, int init_buf, int forcing_bu
         const int n = NVAR * (4 * (c->p.nx + 4) + 4 * c->p.nz);
         copy_halo_ring_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[p_out], c->base[p_forcing], c->L);
         LAUNCHED(c, "copy_halo_ring_kernel");
-        c->xhalo_valid[p_out] = false;  // the ring is the image of the OLD interior, as in the reference
+        c->xhalo_valid[p_out] = false;
+        c->xhalo6_valid[p_out] = false;  // the ring is the image of the OLD interior, as in the reference
         c->l2p[out_buf] = p_out;
         c->spare = p_forcing;
         return PMW_OK;
@@ -825,6 +860,7 @@ extern "C" int pmw_evolve_stage(pmw_ctx* c, int direction, int rk_stage, double 
             LAUNCHED(c, "bc_x_kernel");
         }
         c->xhalo_valid[p_forcing] = true;
+        c->xhalo6_valid[p_forcing] = false;
     }
     // Halo images are stored by the stage whose output the next x stage reads: x stages 1 and 2,
     // and every stage 3 (the next sweep may be an x sweep).  z stages 1 and 2 feed z stages only.
@@ -866,6 +902,7 @@ static int evolve_sweep_chunked(pmw_ctx* c, int direction, double dt)
         bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[S], c->L);
         LAUNCHED(c, "bc_x_kernel");
         c->xhalo_valid[S] = true;
+        c->xhalo6_valid[S] = false;
     }
     CU_TRY(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < K; ++k) CU_TRY(cudaStreamWaitEvent(c->cstream[k], c->ev_fork, 0));
@@ -893,6 +930,132 @@ static int evolve_sweep_chunked(pmw_ctx* c, int direction, double dt)
     return PMW_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused sweeps (pmw_sweep.cuh): one kernel per directional sweep
+// ---------------------------------------------------------------------------------------------
+static bool fuse_ok(const pmw_ctx* c)
+{
+    return c->fuse && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && c->p.nx >= 16 && c->p.nz >= 8 &&
+           !c->src_w && !c->timing;
+}
+
+// Rows per z-sweep segment: a warp (32 columns x lz rows) is the unit of work and every SM holds
+// kZWarps of them; pick the segment count that fills whole waves with the least recomputation.
+static const int kZWarpsPerSM = 8;
+static int pick_sweep_lz(const pmw_ctx* c)
+{
+    if (c->sweep_lz) return std::min(c->sweep_lz, c->p.nz);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
+    const long long strips = (c->p.nx + ZS_COLS - 1) / ZS_COLS;
+    const long long slots = (long long)nsm * kZWarpsPerSM;
+    double best = 1e300;
+    int best_lz = c->p.nz;
+    for (int nseg = 1; nseg <= c->p.nz / 8; ++nseg) {
+        const int lz = (c->p.nz + nseg - 1) / nseg;
+        if ((c->p.nz + lz - 1) / lz != nseg) continue;
+        const long long warps = strips * nseg;
+        const long long waves = (warps + slots - 1) / slots;
+        // time ~ waves x (work of one warp, with the recomputed rows) x (how full the SMs are)
+        const double per_warp = 3.0 * lz + 12.0 + 14.0;  // interface evaluations + pipeline fill
+        const double occupancy = (double)warps / (waves * slots);
+        const double t = waves * per_warp * (0.35 + 0.65 * std::max(occupancy, 0.5));
+        if (t < best) { best = t; best_lz = lz; }
+    }
+    return best_lz;
+}
+
+static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool write_tmp, double dt)
+{
+    NEED(c->hydro_set, "sweep: hydrostatic profiles not set (pmw_set_hydrostatic)");
+    SweepArgs a;
+    a.L = c->L;
+    a.state = c->base[pS];
+    a.out = c->base[pO];
+    a.tmp = c->base[pT];
+    a.hy = c->hy;
+    const double d = (direction == PMW_DIR_X) ? c->p.dx : c->p.dz;
+    a.hv_coeff = -HV_BETA * d / (16 * c->p.dt);
+    a.inv_d = 1.0 / d;
+    a.dt1 = dt / 3;
+    a.dt2 = dt / 2;
+    a.dt3 = dt / 1;
+    a.periodic = c->p.periodic_x ? 1 : 0;
+    a.lz = 0;
+    a.tile_x0 = a.tile_y0 = 0;
+    a.flags = c->flags;
+    a.wait_epoch = a.push_epoch = 0;
+    a.edge_last = 0;
+    a.nbr_state_left = a.nbr_state_right = nullptr;
+    a.nbr_flags_left = a.nbr_flags_right = nullptr;
+    a.push_counter = c->edge_counters;
+    a.dbg = c->peer_dbg;
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+    const CUtensorMap* tm = nullptr;
+    int rc;
+    if (direction == PMW_DIR_X) {
+        if (c->peers) {
+            a.push_epoch = a.wait_epoch = ++c->epoch;
+            a.edge_last = 1;
+            a.nbr_state_left = c->nbr_base[0][pS];
+            a.nbr_state_right = c->nbr_base[1][pS];
+            a.nbr_flags_left = c->nbr_flags[0];
+            a.nbr_flags_right = c->nbr_flags[1];
+        } else if (!c->xhalo6_valid[pS]) {
+            NEED(c->p.periodic_x, "pmw_evolve: the x halo of the state is stale on a slab context without peers");
+            const int n = NVAR * c->p.nz * 6;
+            bc_x6_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[pS], c->L);
+            LAUNCHED(c, "bc_x6_kernel");
+            c->xhalo_valid[pS] = c->xhalo6_valid[pS] = true;
+        }
+        const int P = c->sweep_xp;
+        const int LC = 64 * P - 10;
+        if ((rc = get_tmap(c, pS, 64 * P + 4, 4, &tm, true)) != PMW_OK) return rc;
+        const dim3 grid((c->p.nx + LC - 1) / LC, (c->p.nz + 3) / 4 + (a.push_epoch ? 1 : 0));
+#define GO(PP, PM, WT)                                                                                  \
+    do {                                                                                                \
+        using T = XSweepTile<4, PP>;                                                                    \
+        static unsigned long long attr_done = 0;                                                        \
+        if (!(attr_done >> c->p.device & 1ull)) {                                                       \
+            if ((rc = set_smem(sweep_x<4, PP, PM, WT>, T::smem_bytes())) != PMW_OK) return rc;          \
+            attr_done |= 1ull << c->p.device;                                                           \
+        }                                                                                               \
+        launch_ex(sweep_x<4, PP, PM, WT>, grid, dim3(T::THREADS), T::smem_bytes(), c->stream, c->pdl != 0, *tm, a); \
+    } while (0)
+#define GO_P(PM, WT) do { if (P == 2) GO(2, PM, WT); else GO(3, PM, WT); } while (0)
+        if (fast) { if (write_tmp) GO_P(1, true); else GO_P(1, false); }
+        else      { if (write_tmp) GO_P(0, true); else GO_P(0, false); }
+#undef GO_P
+#undef GO
+        LAUNCHED(c, "sweep_x");
+    } else {
+        a.lz = pick_sweep_lz(c);
+        if ((rc = get_tmap(c, pS, ZS_COLS, 1, &tm, true)) != PMW_OK) return rc;
+        const dim3 grid((c->p.nx + ZS_COLS - 1) / ZS_COLS, (c->p.nz + a.lz - 1) / a.lz);
+#define GO(PM, WT) launch_ex(sweep_z<PM, WT>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl != 0, *tm, a)
+        if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
+        else      { if (write_tmp) GO(0, true); else GO(0, false); }
+#undef GO
+        LAUNCHED(c, "sweep_z");
+    }
+    // S' carries the periodic images of its own edge columns (single slab); in a ring they are pushed
+    // by the next x sweep
+    c->xhalo_valid[pO] = c->xhalo6_valid[pO] = (c->p.periodic_x != 0);
+    return PMW_OK;
+}
+
+static int evolve_sweep_fused(pmw_ctx* c, int direction, double dt, bool write_tmp)
+{
+    if (dt <= 0) dt = c->p.dt;
+    const int S = c->l2p[PMW_BUF_STATE], T = c->l2p[PMW_BUF_TMP], O = c->spare;
+    int rc = launch_sweep(c, direction, S, O, T, write_tmp, dt);
+    if (rc != PMW_OK) return rc;
+    c->l2p[PMW_BUF_STATE] = O;
+    c->spare = S;
+    if (write_tmp) c->xhalo_valid[T] = c->xhalo6_valid[T] = false;
+    return PMW_OK;
+}
+
 extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
 {
     BIND(c);
@@ -902,11 +1065,15 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
          "stage with pmw_evolve_stage and a halo exchange before every x stage");
     // (x sweeps of a connected slab carry the halo push / epoch wait per stage: those stay whole)
     const bool chunk_ok = c->chunks > 1 && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && !c->timing;
+    const bool fused = fuse_ok(c);
     for (int n = 0; n < nsteps; ++n) {
         const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
         for (int d = 0; d < 2; ++d) {
             int rc = PMW_OK;
-            if (chunk_ok && (!c->peers || dirs[d] == PMW_DIR_Z)) {
+            if (fused) {
+                // state_tmp (the reference's stage-2 array) is only materialised by the last sweep of the call
+                rc = evolve_sweep_fused(c, dirs[d], dt, c->keep_tmp && n == nsteps - 1 && d == 1);
+            } else if (chunk_ok && (!c->peers || dirs[d] == PMW_DIR_Z)) {
                 rc = evolve_sweep_chunked(c, dirs[d], dt);
             } else {
                 for (int s = 1; s <= 3 && rc == PMW_OK; ++s) rc = pmw_evolve_stage(c, dirs[d], s, dt);
@@ -1005,6 +1172,7 @@ extern "C" int pmw_unpack_halo_x(pmw_ctx* c, int buf, const double* from_left, c
     unpack_halo_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, from_left, from_right);
     LAUNCHED(c, "unpack_halo_x_kernel");
     c->xhalo_valid[c->l2p[buf]] = true;
+    c->xhalo6_valid[c->l2p[buf]] = false;
     return PMW_OK;
 }
 
@@ -1103,7 +1271,7 @@ extern "C" int pmw_connect_peers(pmw_ctx* c, void* const left[4], void* const ri
     c->epoch = 0;
     CU_TRY(cudaMemsetAsync(c->flags, 0, 4 * sizeof(unsigned long long), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    for (int b = 0; b < 3; ++b) c->xhalo_valid[b] = false;
+    for (int b = 0; b < 3; ++b) c->xhalo_valid[b] = c->xhalo6_valid[b] = false;
     return PMW_OK;
 }
 

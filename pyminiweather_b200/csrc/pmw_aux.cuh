@@ -18,6 +18,19 @@ __global__ void bc_x_kernel(double* s, const Layout L)
     row[nx + HS + 1] = row[HS + 1];
 }
 
+// The same periodic wrap, six columns wide: what a fused x sweep (pmw_sweep.cuh) reads.  Array
+// columns -4 .. 1 are the image of nx-4 .. nx+1, columns nx+2 .. nx+7 the image of 2 .. 7.
+__global__ void bc_x6_kernel(double* s, const Layout L)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NVAR * L.nz * 6) return;
+    const int j = t % 6, k = (t / 6) % L.nz + HS, v = t / (6 * L.nz);
+    double* row = s + idx(L, v, k, 0);
+    const int nx = L.nx;
+    row[j - 4] = row[nx + j - 4];
+    row[nx + HS + j] = row[HS + j];
+}
+
 // set_bc_z (bcs.py:92-148): all nx+4 columns.  True divisions, in the reference's order.
 __global__ void bc_z_kernel(double* s, const Layout L, const double* __restrict__ hd)
 {

@@ -11,6 +11,9 @@
 // 16 doubles (128 B) and vstride = pitch * (nz+4).
 #pragma once
 #include <cuda_runtime.h>
+#ifndef PMW_RCP_ITERS
+#define PMW_RCP_ITERS 3
+#endif
 #include <stdint.h>
 
 namespace pmw {
@@ -128,23 +131,62 @@ __device__ __forceinline__ void push_halo_role(const StageArgs& a)
 // ((1+e)^gamma-1)/e, truncation error 7e-20, evaluated as two interleaved Horner chains in
 // e^2; absolute error <= 4e-17 measured against mpmath).  Used by PMW_POW_BACKGROUND.
 // ---------------------------------------------------------------------------------
+// The coefficients live in the constant bank so that they are direct operands of the DFMAs (as
+// immediates every one of them costs two UMOVs per use: 17 % of the instructions of a fused sweep).
+__constant__ double kPow1p[13] = {
+    0x1.6678ae3cb2859p+0,    // c0
+    0x1.1efa23f1c08bdp-2,    // c1
+    -0x1.caf32d76b8de6p-5,   // c2
+    0x1.6f188e3a61d00p-6,    // c3
+    -0x1.7dbd21dc9b33fp-7,   // c4
+    0x1.ca0d1259f841dp-8,    // c5
+    -0x1.2cfc9a56ff6c7p-8,   // c6
+    0x1.a55c83fc9dc65p-9,    // c7
+    -0x1.34fc42d60dfbcp-9,   // c8
+    0x1.d56fc4d94646ap-10,   // c9
+    -0x1.6efd8124188fdp-10,  // c10
+    0x1.300687b793e42p-10,   // c11
+    -0x1.f04c6e36150e8p-11,  // c12
+};
+__constant__ double kInterp[2] = {-1.0 / 12, 7.0 / 12};  // fields.py:94-96
+__constant__ double kGrav = GRAV;
+
 __device__ __forceinline__ double pow1p_gamma_m1(double e)
 {
     const double e2 = e * e;
-    double a = -0x1.f04c6e36150e8p-11;        // c12
-    double b = 0x1.300687b793e42p-10;         // c11
-    a = fma(a, e2, -0x1.6efd8124188fdp-10);   // c10
-    b = fma(b, e2, 0x1.d56fc4d94646ap-10);    // c9
-    a = fma(a, e2, -0x1.34fc42d60dfbcp-9);    // c8
-    b = fma(b, e2, 0x1.a55c83fc9dc65p-9);     // c7
-    a = fma(a, e2, -0x1.2cfc9a56ff6c7p-8);    // c6
-    b = fma(b, e2, 0x1.ca0d1259f841dp-8);     // c5
-    a = fma(a, e2, -0x1.7dbd21dc9b33fp-7);    // c4
-    b = fma(b, e2, 0x1.6f188e3a61d00p-6);     // c3
-    a = fma(a, e2, -0x1.caf32d76b8de6p-5);    // c2
-    b = fma(b, e2, 0x1.1efa23f1c08bdp-2);     // c1
-    a = fma(a, e2, 0x1.6678ae3cb2859p+0);     // c0
+    double a = kPow1p[12];
+    double b = kPow1p[11];
+    a = fma(a, e2, kPow1p[10]);
+    b = fma(b, e2, kPow1p[9]);
+    a = fma(a, e2, kPow1p[8]);
+    b = fma(b, e2, kPow1p[7]);
+    a = fma(a, e2, kPow1p[6]);
+    b = fma(b, e2, kPow1p[5]);
+    a = fma(a, e2, kPow1p[4]);
+    b = fma(b, e2, kPow1p[3]);
+    a = fma(a, e2, kPow1p[2]);
+    b = fma(b, e2, kPow1p[1]);
+    a = fma(a, e2, kPow1p[0]);
     return fma(b, e, a) * e;
+}
+
+// 1/x for normal, positive x (densities): MUFU.RCP64H seed (>= 20 good bits) and Newton steps.
+// Straight-line code -- __drcp_rn carries a branch for special operands, which splits the basic
+// block of every interface evaluation and keeps the scheduler from interleaving independent
+// evaluations.  Correctly rounded except for rare near-ties (tools/arith_probe/rcp_probe.cu).
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+#if PMW_RCP_ITERS >= 3
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+#endif
+    return r;
 }
 
 // Everything one interface needs besides the 4x4 stencil values.
@@ -171,7 +213,7 @@ __device__ __forceinline__ void interface_flux(const double (&s0)[4], const doub
                                                const IfaceBg& bg, double hv, bool wall,
                                                double (&flux)[4])
 {
-    constexpr double c0 = -1.0 / 12, c1 = 7.0 / 12;
+    const double c0 = kInterp[0], c1 = kInterp[1];
     double val[4], d3[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -179,7 +221,7 @@ __device__ __forceinline__ void interface_flux(const double (&s0)[4], const doub
         d3[v] = fma(-3.0, s2[v], fma(3.0, s1[v], -s0[v])) + s3[v];
     }
     const double rho = val[DENS] + bg.dens;
-    const double r = __drcp_rn(rho);
+    const double r = rcp_pos(rho);
     const double u = val[UMOM] * r;
     double w = val[WMOM] * r;
     const double t = (val[RHOT] + bg.dens_theta) * r;
@@ -212,6 +254,71 @@ __device__ __forceinline__ void interface_flux(const double (&s0)[4], const doub
         flux[WMOM] = fma(-hv, d3[WMOM], ru * w);
         flux[RHOT] = fma(-hv, d3[RHOT], ru * t);
     }
+}
+
+// The same evaluation without the range branch of the background-relative pressure: always the
+// polynomial; returns true when |e| > 1/8 (or NaN), in which case `flux` must be recomputed with
+// interface_flux.  The fused sweeps evaluate several interfaces per iteration and test all their
+// flags with one warp vote instead of one divergent branch per interface.  Identical operations in
+// identical order: where it returns false the result has the same bits as interface_flux.
+template <bool DIR_Z, int POW_MODE>
+__device__ __forceinline__ bool interface_flux_fast(const double (&s0)[4], const double (&s1)[4],
+                                                    const double (&s2)[4], const double (&s3)[4],
+                                                    const IfaceBg& bg, double hv, bool wall,
+                                                    double (&flux)[4])
+{
+    if (POW_MODE != 1) {
+        interface_flux<DIR_Z, POW_MODE>(s0, s1, s2, s3, bg, hv, wall, flux);
+        return false;
+    }
+    const double c0 = kInterp[0], c1 = kInterp[1];
+    double val[4], d3[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        val[v] = fma(c0, s3[v], fma(c1, s2[v], fma(c1, s1[v], c0 * s0[v])));
+        d3[v] = fma(-3.0, s2[v], fma(3.0, s1[v], -s0[v])) + s3[v];
+    }
+    const double rho = val[DENS] + bg.dens;
+    const double r = rcp_pos(rho);
+    const double u = val[UMOM] * r;
+    double w = val[WMOM] * r;
+    const double t = (val[RHOT] + bg.dens_theta) * r;
+    const double rt = rho * t;
+    const double e = (rt - bg.dens_theta) * bg.inv_dens_theta;
+    const double f = pow1p_gamma_m1(e);
+    const double p = DIR_Z ? bg.pressure * f : fma(bg.pressure, f, bg.pressure);
+    if (DIR_Z) {
+        if (wall) { w = 0.0; d3[DENS] = 0.0; }
+        const double rw = rho * w;
+        flux[DENS] = fma(-hv, d3[DENS], rw);
+        flux[UMOM] = fma(-hv, d3[UMOM], rw * u);
+        flux[WMOM] = fma(-hv, d3[WMOM], fma(rho, w * w, p));
+        flux[RHOT] = fma(-hv, d3[RHOT], rw * t);
+    } else {
+        const double ru = rho * u;
+        flux[DENS] = fma(-hv, d3[DENS], ru);
+        flux[UMOM] = fma(-hv, d3[UMOM], fma(rho, u * u, p));
+        flux[WMOM] = fma(-hv, d3[WMOM], ru * w);
+        flux[RHOT] = fma(-hv, d3[RHOT], ru * t);
+    }
+    return !(fabs(e) <= 0.125);
+}
+
+// Out-of-line fallback of the fused sweeps (rare: |e| > 1/8 somewhere in the warp).
+struct Taps {
+    double s[4][4];
+};
+struct Flux4 {
+    double f[4];
+};
+// Arguments and result by value: nothing of the caller's is address-taken, so its flux arrays stay
+// in registers on the hot path.
+template <bool DIR_Z, int POW_MODE>
+__device__ __noinline__ Flux4 interface_flux_slow(Taps t, IfaceBg bg, double hv, bool wall)
+{
+    Flux4 r;
+    interface_flux<DIR_Z, POW_MODE>(t.s[0], t.s[1], t.s[2], t.s[3], bg, hv, wall, r.f);
+    return r;
 }
 
 // Wall halo value for set_bc_z folded into a z stage (bcs.py:92-148): `interior` is the

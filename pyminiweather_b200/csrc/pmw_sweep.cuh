@@ -1,0 +1,562 @@
+// Fused directional sweeps: all three low-storage RK stages of one direction (step.py:112-141)
+// in ONE kernel, with the two intermediate states kept on chip.
+//
+// The three stages of a sweep only couple cells along the sweep direction:
+//     T1  = S + dt/3 * T(S)        T2 = S + dt/2 * T(T1)        S' = S + dt * T(T2)
+// so a tile that carries a 6-cell halo along that direction (2 cells per stage) can run all of
+// them without touching HBM in between: the state is read once and written once per sweep,
+// 64 B/cell instead of the 256 B/cell the stage-by-stage kernels move.  At that traffic the
+// sweep is no longer HBM-bound on B200 but bound by the FP64 pipe (~95 FP64 instructions per
+// cell-stage), so the kernels below are organised around instruction count and FP64 issue, not
+// around bytes.  The arithmetic per cell-stage is interface_flux + the same update expressions as
+// the stage kernels (pmw_tma.cuh): results are bit-identical to the stage-by-stage path, halo
+// cells of the intermediate states are simply recomputed by the neighbouring tile.
+//
+// x sweep (sweep_x).  A CTA owns TR rows x L = 64P-10 cells; one TMA box load brings the state
+// tile with its 6-column halo (64P+4 columns).  Afterwards every WARP is autonomous: it owns one
+// row, runs stage 1 over 64P-2 cells into a shared-memory row T1, stage 2 over 64P-6 cells into
+// T2, stage 3 over its 64P-10 owned cells straight to HBM -- each stage with the pass structure
+// of stage_x_tma (two interfaces per lane, the third flux by a rotating shuffle), separated only
+// by __syncwarp.  Periodic x: the halo columns are the 6-wide image of the opposite edge, written
+// by whichever sweep produced the state (set_bc_x, bcs.py:35-39, folded into the producer).
+//
+// z sweep (sweep_z).  A warp owns a strip of 32 columns (one per lane) and streams upwards through
+// a segment of LZ rows: per iteration it advances THREE software-pipelined interface evaluations
+// -- stage 1 at interface j, stage 2 at j-3, stage 3 at j-6 -- whose 4-row stencil windows live
+// in registers and are fed by the stage below (T1 and T2 never leave the register file).  The
+// three evaluations of an iteration are independent (ILP 3).  State rows arrive through a 16-slot
+// ring of 1 KB TMA boxes (one mbarrier per slot, issued 6 rows ahead by lane 0); the ring also
+// serves the initial-state reads of stages 2 and 3.  Solid-wall halo rows (set_bc_z,
+// bcs.py:92-148) are rebuilt in the register windows, so halo rows are never read.  A segment
+// recomputes 4 + 2 rows of T1 / T2 on either side (none at a wall).
+#pragma once
+#include "pmw_tma.cuh"
+
+namespace pmw {
+
+constexpr int SWEEP_HALO = 6;  // x halo columns a fused x sweep reads (3 stages x 2 cells)
+
+struct SweepArgs {
+    Layout L;
+    const double* state;  // S  (x sweeps: with a valid 6-wide x halo)
+    double* out;          // S' (a different buffer: neighbouring tiles still read S)
+    double* tmp;          // T2 of the owned cells when WRITE_TMP (the reference's state_tmp), else unused
+    Hydro hy;
+    double hv_coeff;  // -hv_beta*d/(16*dt_full)   (interpolate.py:101,149)
+    double inv_d;     // 1/dx or 1/dz
+    double dt1, dt2, dt3;  // dt/3, dt/2, dt
+    int periodic;     // also store the 6-wide periodic images of the edge columns of S'
+    int lz;           // z sweep: rows per segment
+    int tile_x0, tile_y0;
+    // slab ring (x sweeps): see StageArgs
+    unsigned long long* flags;
+    unsigned long long wait_epoch, push_epoch;
+    int edge_last;
+    double* nbr_state_left;
+    double* nbr_state_right;
+    unsigned long long* nbr_flags_left;
+    unsigned long long* nbr_flags_right;
+    unsigned int* push_counter;
+    int dbg;
+};
+
+// Slab ring, fused x sweep: the first row of CTAs stores this slab's own six edge columns of S
+// into the neighbours' halo columns and publishes push_epoch (cf. push_halo_role).
+__device__ __forceinline__ void push_halo6_role(const SweepArgs& a)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const Layout& L = a.L;
+    const int per_row = SWEEP_HALO / 2;  // column pairs per side
+    for (int t = blockIdx.x * nthr + tid; t < NVAR * L.nz * per_row; t += gridDim.x * nthr) {
+        const int j = t % per_row, k = (t / per_row) % L.nz, v = t / (per_row * L.nz);
+        const double2 first = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, HS + 2 * j));
+        const double2 last =
+            *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, L.nx + HS - SWEEP_HALO + 2 * j));
+        // our first columns are the left neighbour's right halo; our last columns the right neighbour's left halo
+        *reinterpret_cast<double2*>(a.nbr_state_left + idx(L, v, k + HS, L.nx + HS + 2 * j)) = first;
+        *reinterpret_cast<double2*>(a.nbr_state_right + idx(L, v, k + HS, HS - SWEEP_HALO + 2 * j)) = last;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && atomicAdd(a.push_counter, 1u) == gridDim.x - 1) {
+        *a.push_counter = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.nbr_flags_left + 1), "l"(a.push_epoch) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.nbr_flags_right + 0), "l"(a.push_epoch) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x sweep
+// ------------------------------------------------------------------------------------------
+template <int TR, int P>
+struct XSweepTile {
+    static constexpr int FW = 64 * P + 4;   // tile columns (state box width)
+    static constexpr int LC = 64 * P - 10;  // owned cells per row
+    static constexpr int ELEMS = NVAR * TR * FW;
+    static constexpr int THREADS = 32 * TR;
+    static constexpr size_t smem_bytes() { return (size_t)3 * ELEMS * sizeof(double) + 16; }
+};
+
+// Both interface fluxes of a lane's pair with ONE warp-uniform fallback branch (see
+// interface_flux_fast).
+template <int POW_MODE>
+__device__ __forceinline__ void xpair_flux(const double (&t0)[4], const double (&t1)[4], const double (&t2)[4],
+                                           const double (&t3)[4], const double (&t4)[4], const IfaceBg& bg, double hv,
+                                           double (&f0)[4], double (&f1)[4])
+{
+    const bool bad0 = interface_flux_fast<false, POW_MODE>(t0, t1, t2, t3, bg, hv, false, f0);
+    const bool bad1 = interface_flux_fast<false, POW_MODE>(t1, t2, t3, t4, bg, hv, false, f1);
+    if (__any_sync(0xffffffffu, bad0 || bad1)) {
+        asm volatile("" ::: "memory");  // keep the argument copies of the cold path inside the branch
+        Taps T;
+        if (bad0) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { T.s[0][v] = t0[v]; T.s[1][v] = t1[v]; T.s[2][v] = t2[v]; T.s[3][v] = t3[v]; }
+            const Flux4 g = interface_flux_slow<false, POW_MODE>(T, bg, hv, false);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) f0[v] = g.f[v];
+        }
+        if (bad1) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { T.s[0][v] = t1[v]; T.s[1][v] = t2[v]; T.s[2][v] = t3[v]; T.s[3][v] = t4[v]; }
+            const Flux4 g = interface_flux_slow<false, POW_MODE>(T, bg, hv, false);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) f1[v] = g.f[v];
+        }
+    }
+}
+
+// The three stages and the passes of a stage run through ONE copy of the pass body (runtime loops):
+// the whole kernel stays inside the instruction cache.  Tile column t holds interior column c0-6+t.
+template <int TR, int P, int POW_MODE, bool WRITE_TMP>
+__global__ void __launch_bounds__(32 * TR, (P == 2 && TR == 4) ? 4 : 1)
+sweep_x(const __grid_constant__ CUtensorMap tm_state, const SweepArgs a)
+{
+    using T = XSweepTile<TR, P>;
+    constexpr int VS = TR * T::FW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sS = reinterpret_cast<double*>(smem_raw);
+    double* sT1 = sS + T::ELEMS;
+    double* sT2 = sT1 + T::ELEMS;
+    static_assert((T::ELEMS * 8) % 128 == 0, "tiles stay 128-byte aligned");
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + T::ELEMS);
+
+    const int ntx = gridDim.x;
+    const int push_rows = a.push_epoch ? 1 : 0;
+    const int nty = gridDim.y - push_rows;
+    if (push_rows && blockIdx.y == 0) {
+        pdl_launch_dependents();
+        pdl_wait();
+        push_halo6_role(a);
+        return;
+    }
+    int tx = blockIdx.x, ty = blockIdx.y - push_rows;
+    if (a.edge_last) {  // slab ring: the tile columns that read neighbour halos are the last CTAs
+        const int lin = ty * ntx + tx;
+        const int cidx = lin / nty;
+        ty = lin % nty;
+        tx = (cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1);
+    }
+    ty += a.tile_y0;
+    const int nx = a.L.nx, nz = a.L.nz;
+    const int c0 = tx * T::LC;  // first owned interior column (even)
+    const int r0 = ty * TR;
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_state);
+        mbar_init(bar, 1);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // columns of T1 / T2 that no stage writes but the next stage's (discarded) edge interfaces read
+    {
+        double* r1 = sT1 + warp * T::FW;
+        double* r2 = sT2 + warp * T::FW;
+        if (lane < 16) {
+            const int v = lane >> 2, j = lane & 3;
+            if (j < 2) r1[v * VS + j] = 0.0;
+            r1[v * VS + 64 * P + j] = 0.0;
+            r2[v * VS + j] = 0.0;
+            r2[v * VS + 64 * P + j] = 0.0;
+            if (j < 2) r2[v * VS + 64 * P - 2 + j] = 0.0;
+        }
+    }
+    __syncthreads();
+    pdl_wait();  // everything below reads state produced by the previous kernel
+    if (threadIdx.x == 0) {
+        if (a.wait_epoch && !(a.dbg & 2)) {
+            if (c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
+            if (c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
+        }
+        mbar_arrive_expect_tx(bar, (uint32_t)(T::ELEMS * sizeof(double)));
+        // map column 0 is interior column -6 (array column -4)
+        tma_load_3d(sS, &tm_state, c0, r0 + HS, 0, bar, l2_policy(1));
+    }
+    const int k = r0 + warp;
+    const bool row_ok = k < nz;
+    const int kc = min(k, nz - 1);
+    const IfaceBg bg = bg_x(a.hy, kc + HS);
+    // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
+    // q only matters while 64q <= that limit (warp-uniform)
+    const int rem = min(nx - c0, T::LC);
+    const double* rowS = sS + warp * T::FW + 2 * lane;
+    double* const po = a.out + idx(a.L, 0, kc + HS, c0 - SWEEP_HALO + HS + 2 * lane);
+    double* const pt = a.tmp + idx(a.L, 0, kc + HS, c0 - SWEEP_HALO + HS + 2 * lane);
+    const int src_lane = (lane + 1) & 31;
+    const int i0 = c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
+    mbar_wait(bar, 0);
+
+    const double* src = rowS;
+    double* dst = sT1 + warp * T::FW + 2 * lane;
+    double dts = a.dt1;
+    int tlo = 2, thi = 64 * P;
+#pragma unroll 1
+    for (int s = 0; s < 3; ++s) {
+        const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
+        double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
+#pragma unroll 1
+        for (int q = nq - 1; q >= 0; --q) {
+            double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const double* p = src + v * VS + 64 * q;
+                const Pair u01 = lds2(p), u23 = lds2(p + 2);
+                t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
+            }
+            xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
+            const int t = 64 * q + 2 * lane + 2;  // tile column of the left cell of the pair
+            const int i = i0 + 64 * q;
+            bool ok = t >= tlo && t < thi;
+            if (s == 2) ok = ok && row_ok && i < nx;
+            double xa[4], xb[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const double give = (lane == 0) ? keep[v] : f0[v];
+                const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
+                keep[v] = f0[v];
+                double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
+                if (s != 0) {
+                    const Pair in = lds2(rowS + v * VS + 64 * q + 2);
+                    ia = in.a; ib = in.b;
+                }
+                const double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                xa[v] = fma(dts, ta, ia);
+                xb[v] = fma(dts, tb, ib);
+            }
+            if (ok) {
+                if (s != 2) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        *reinterpret_cast<double2*>(dst + v * VS + 64 * q + 2) = make_double2(xa[v], xb[v]);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const long long o = v * a.L.vstride + 64 * q + 2;
+                        *reinterpret_cast<double2*>(po + o) = make_double2(xa[v], xb[v]);
+                        if (a.periodic) {
+                            if (i < SWEEP_HALO) *reinterpret_cast<double2*>(po + o + nx) = make_double2(xa[v], xb[v]);
+                            if (i >= nx - SWEEP_HALO) *reinterpret_cast<double2*>(po + o - nx) = make_double2(xa[v], xb[v]);
+                        }
+                        if (WRITE_TMP) *reinterpret_cast<double2*>(pt + o) = make_double2(t2[v], t3[v]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        src = (s == 0) ? sT1 + warp * T::FW + 2 * lane : sT2 + warp * T::FW + 2 * lane;
+        dst = sT2 + warp * T::FW + 2 * lane;
+        dts = (s == 0) ? a.dt2 : a.dt3;
+        tlo += 2;
+        thi -= 2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// z sweep
+// ------------------------------------------------------------------------------------------
+constexpr int ZS_COLS = 32;   // columns per strip (one per lane)
+constexpr int ZS_RING = 16;   // state rows resident per warp
+constexpr int ZS_AHEAD = 6;   // rows requested ahead of the newest row in use
+constexpr int ZS_ROW = NVAR * ZS_COLS;  // doubles per ring slot
+constexpr size_t zsweep_smem_bytes() { return (size_t)ZS_RING * ZS_ROW * sizeof(double) + ZS_RING * 8; }
+
+// Register window of one stage: the forcing cells k-2 .. k+1 of interface k, [slot][variable].
+// The generic path keeps tap t in slot t and shifts; the steady-state path rotates instead (tap t
+// of a stage whose window is at rotation R lives in slot (R+t)&3; four iterations, unrolled, bring
+// the rotation back to 0), so that no register is ever moved.
+template <int POW_MODE>
+struct ZStage {
+    double W[4][4];
+    double fprev[4];  // flux through interface k-1
+
+    // Generic step (warp-uniform branches for walls): evaluate interface k from slots 0..3 and
+    // finalise cell k-1 = init + dt*tendency.
+    __device__ __forceinline__ void step(const SweepArgs& a, int k, double dt_stage, const double (&init)[4],
+                                         double (&cell)[4])
+    {
+        const int nz = a.L.nz;
+        const double* hd = a.hy.dens_cell;
+        if (k == 0) {  // set_bc_z, bottom rows (bcs.py:92-148) from interior row 0 = tap 2
+            const double h2 = __ldg(hd + HS), h0 = __ldg(hd), h1 = __ldg(hd + 1);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                W[0][v] = wall_value(v, W[2][v], h2, h0);
+                W[1][v] = wall_value(v, W[2][v], h2, h1);
+            }
+        }
+        if (k == nz - 1) {  // top halo row nz+2 from interior row nz-1 = tap 2
+            const double hi = __ldg(hd + nz + HS - 1), h = __ldg(hd + nz + HS);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) W[3][v] = wall_value(v, W[2][v], hi, h);
+        }
+        if (k == nz) {  // interior row nz-1 = tap 1
+            const double hi = __ldg(hd + nz + HS - 1), h2 = __ldg(hd + nz + HS), h3 = __ldg(hd + nz + HS + 1);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                W[2][v] = wall_value(v, W[1][v], hi, h2);
+                W[3][v] = wall_value(v, W[1][v], hi, h3);
+            }
+        }
+        const bool wall = (k == 0 || k == nz);
+        const IfaceBg bg = bg_z(a.hy, k);
+        double f[4];
+        interface_flux<true, POW_MODE>(W[0], W[1], W[2], W[3], bg, a.hv_coeff, wall, f);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            double t = (fprev[v] - f[v]) * a.inv_d;
+            if (v == WMOM) t = fma(-W[1][DENS], GRAV, t);  // hydrostatic source (interpolate.py:248-250)
+            cell[v] = fma(dt_stage, t, init[v]);
+            fprev[v] = f[v];
+        }
+    }
+    __device__ __forceinline__ void push(const double (&row)[4])
+    {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            W[0][v] = W[1][v]; W[1][v] = W[2][v]; W[2][v] = W[3][v]; W[3][v] = row[v];
+        }
+    }
+
+    // Steady state, rotation R0 (tap t in slot (R0+t)&3): flux of interior interface k.
+    template <int R0>
+    __device__ __forceinline__ bool flux_fast(const SweepArgs& a, const IfaceBg& bg, double (&f)[4])
+    {
+        return interface_flux_fast<true, POW_MODE>(W[R0 & 3], W[(R0 + 1) & 3], W[(R0 + 2) & 3], W[(R0 + 3) & 3], bg,
+                                                   a.hv_coeff, false, f);
+    }
+    template <int R0>
+    __device__ __forceinline__ void flux_slow(const SweepArgs& a, const IfaceBg& bg, double (&f)[4])
+    {
+        Taps T;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) T.s[t][v] = W[(R0 + t) & 3][v];
+        const Flux4 g = interface_flux_slow<true, POW_MODE>(T, bg, a.hv_coeff, false);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) f[v] = g.f[v];
+    }
+    // cell k-1 (tap 1) from the fluxes through its two faces
+    template <int R0>
+    __device__ __forceinline__ void finish(const SweepArgs& a, const double (&f)[4], double dt_stage,
+                                           const double (&init)[4], double (&cell)[4])
+    {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            double t = (fprev[v] - f[v]) * a.inv_d;
+            if (v == WMOM) t = fma(-W[(R0 + 1) & 3][DENS], GRAV, t);
+            cell[v] = fma(dt_stage, t, init[v]);
+            fprev[v] = f[v];
+        }
+    }
+};
+
+struct ZStream {  // per-warp constants of the state-row stream
+    double* ring;
+    uint64_t* bars;
+    const CUtensorMap* tm;
+    int f0, last_cell, c0, lane;
+    unsigned long long pol;
+    __device__ __forceinline__ void request(int m) const  // lane 0: start the load of state cell row m
+    {
+        if (m <= last_cell) {
+            const int s = (m - f0) & (ZS_RING - 1);
+            mbar_arrive_expect_tx(bars + s, (uint32_t)(ZS_ROW * sizeof(double)));
+            tma_load_3d(ring + s * ZS_ROW, tm, c0 + HS + 4, m + HS, 0, bars + s, pol);
+        }
+    }
+    __device__ __forceinline__ const double* row(int m) const
+    {
+        return ring + ((m - f0) & (ZS_RING - 1)) * ZS_ROW + lane;
+    }
+    __device__ __forceinline__ void wait(int m) const
+    {
+        mbar_wait(bars + ((m - f0) & (ZS_RING - 1)), ((m - f0) >> 4) & 1);
+    }
+};
+
+// One steady-state iteration at window rotation R: stage 1 at interface j, stage 2 at j-3, stage 3
+// at j-6; all interior, all cells valid.  Straight-line code: the three evaluations interleave.
+template <int R, int POW_MODE, bool WRITE_TMP>
+__device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream& zs, ZStage<POW_MODE>& s1,
+                                              ZStage<POW_MODE>& s2, ZStage<POW_MODE>& s3, int j, double* pout,
+                                              double* ptmp, bool col_ok, bool img_r, bool img_l)
+{
+    __syncwarp();  // every lane is done with the rows of the previous iteration
+    if (zs.lane == 0) zs.request(j + 1 + ZS_AHEAD);
+    zs.wait(j + 1);
+    const double* top = zs.row(j + 1);
+    const double* r2 = zs.row(j - 4);
+    const double* r3 = zs.row(j - 7);
+    double in2[4], in3[4], f1[4], f2[4], f3[4], c1[4], c2[4], c3[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        s1.W[R & 3][v] = top[v * ZS_COLS];  // newest state row replaces the oldest: taps now start at slot R+1
+        in2[v] = r2[v * ZS_COLS];
+        in3[v] = r3[v * ZS_COLS];
+    }
+    const IfaceBg bg1 = bg_z(a.hy, j), bg2 = bg_z(a.hy, j - 3), bg3 = bg_z(a.hy, j - 6);
+    const bool bad3 = s3.template flux_fast<R>(a, bg3, f3);
+    const bool bad2 = s2.template flux_fast<R>(a, bg2, f2);
+    const bool bad1 = s1.template flux_fast<R + 1>(a, bg1, f1);
+    if (__any_sync(0xffffffffu, bad1 || bad2 || bad3)) {
+        asm volatile("" ::: "memory");  // keep the argument copies of the cold path inside the branch
+        if (bad3) s3.template flux_slow<R>(a, bg3, f3);
+        if (bad2) s2.template flux_slow<R>(a, bg2, f2);
+        if (bad1) s1.template flux_slow<R + 1>(a, bg1, f1);
+    }
+    if (WRITE_TMP && col_ok) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ptmp[v * a.L.vstride] = s3.W[(R + 1) & 3][v];  // T2 of the cell
+    }
+    s3.template finish<R>(a, f3, a.dt3, in3, c3);
+    s2.template finish<R>(a, f2, a.dt2, in2, c2);
+    s1.template finish<R + 1>(a, f1, a.dt1, s1.W[(R + 2) & 3], c1);
+    if (col_ok) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            double* q = pout + v * a.L.vstride;
+            *q = c3[v];
+            if (img_r) q[a.L.nx] = c3[v];
+            if (img_l) q[-a.L.nx] = c3[v];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {  // the new cells replace the oldest taps
+        s3.W[R & 3][v] = c2[v];
+        s2.W[R & 3][v] = c1[v];
+    }
+}
+
+template <int POW_MODE, bool WRITE_TMP>
+__global__ void __launch_bounds__(32)
+sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ZStream zs;
+    zs.ring = reinterpret_cast<double*>(smem_raw);
+    zs.bars = reinterpret_cast<uint64_t*>(zs.ring + ZS_RING * ZS_ROW);
+    zs.tm = &tm_row;
+
+    const int lane = threadIdx.x;
+    const int nx = a.L.nx, nz = a.L.nz;
+    const int c0 = (blockIdx.x + a.tile_x0) * ZS_COLS;
+    const int i = c0 + lane;
+    const bool col_ok = i < nx;
+    const int lo3 = blockIdx.y * a.lz, hi3 = min(lo3 + a.lz, nz);
+    const int lo2 = max(lo3 - 2, 0), hi2 = min(hi3 + 2, nz);
+    const int lo1 = max(lo3 - 4, 0), hi1 = min(hi3 + 4, nz);
+    zs.f0 = lo1 - 2;          // first state cell row of the stream (array row f0 + 2)
+    zs.last_cell = hi1 + 1;   // last one
+    zs.c0 = c0;
+    zs.lane = lane;
+    pdl_launch_dependents();
+    if (lane == 0) {
+        tma_prefetch_desc(&tm_row);
+        for (int s = 0; s < ZS_RING; ++s) mbar_init(zs.bars + s, 1);
+    }
+    __syncwarp();
+    pdl_wait();
+    zs.pol = l2_policy(1);
+    if (lane == 0)
+        for (int m = zs.f0; m <= zs.f0 + 2 + ZS_AHEAD; ++m) zs.request(m);
+
+    ZStage<POW_MODE> s1, s2, s3;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) s1.W[t][v] = s2.W[t][v] = s3.W[t][v] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) s1.fprev[v] = s2.fprev[v] = s3.fprev[v] = 0.0;
+    for (int m = zs.f0; m <= zs.f0 + 2; ++m) {  // the first three taps of stage 1
+        zs.wait(m);
+        double r[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) r[v] = zs.row(m)[v * ZS_COLS];
+        s1.push(r);
+    }
+    double* const pout0 = a.out + idx(a.L, 0, HS, min(i, nx - 1) + HS);
+    double* const ptmp0 = a.tmp + idx(a.L, 0, HS, min(i, nx - 1) + HS);
+    const bool img_r = a.periodic && i < SWEEP_HALO, img_l = a.periodic && i >= nx - SWEEP_HALO;
+
+    // steady iterations (all three stages active, every cell valid, no wall): js <= j <= je
+    const int js = max(lo3 + 7, 7), je = min(hi1, nz - 2);
+    int j = lo1;
+    while (j <= hi3 + 6) {
+        if (j >= js && j + 3 <= je) {
+            double* po = pout0 + (long long)(j - 7) * a.L.pitch;
+            double* pt = ptmp0 + (long long)(j - 7) * a.L.pitch;
+            const int p = a.L.pitch;
+            zsweep_steady<0, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j, po, pt, col_ok, img_r, img_l);
+            zsweep_steady<1, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j + 1, po + p, pt + p, col_ok, img_r, img_l);
+            zsweep_steady<2, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j + 2, po + 2 * p, pt + 2 * p, col_ok, img_r, img_l);
+            zsweep_steady<3, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j + 3, po + 3 * p, pt + 3 * p, col_ok, img_r, img_l);
+            j += 4;
+            continue;
+        }
+        // generic iteration: segment start / end and walls
+        __syncwarp();
+        if (lane == 0) zs.request(j + 1 + ZS_AHEAD);
+        double top[4], in2[4], in3[4];
+        double c1[4] = {0.0, 0.0, 0.0, 0.0}, c2[4] = {0.0, 0.0, 0.0, 0.0}, c3[4];
+        {
+            const int m = j + 1;  // newest state row: tap 3 of interface j
+            if (m <= zs.last_cell) {
+                zs.wait(m);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) top[v] = zs.row(m)[v * ZS_COLS];
+            } else {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) top[v] = 0.0;
+            }
+            s1.push(top);
+        }
+        const int k1 = j, k2 = j - 3, k3 = j - 6;
+        if (k3 >= lo3 && k3 <= hi3) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) in3[v] = (k3 > lo3) ? zs.row(k3 - 1)[v * ZS_COLS] : 0.0;
+            s3.step(a, k3, a.dt3, in3, c3);
+            if (k3 > lo3 && col_ok) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const long long o = v * a.L.vstride + (long long)(k3 - 1) * a.L.pitch;
+                    pout0[o] = c3[v];
+                    if (img_r) pout0[o + nx] = c3[v];
+                    if (img_l) pout0[o - nx] = c3[v];
+                    if (WRITE_TMP) ptmp0[o] = s3.W[1][v];
+                }
+            }
+        }
+        if (k2 >= lo2 && k2 <= hi2) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) in2[v] = (k2 > lo2) ? zs.row(k2 - 1)[v * ZS_COLS] : 0.0;
+            s2.step(a, k2, a.dt2, in2, c2);
+        }
+        if (k1 <= hi1) s1.step(a, k1, a.dt1, s1.W[1], c1);
+        s3.push(c2);
+        s2.push(c1);
+        ++j;
+    }
+}
+
+}  // namespace pmw

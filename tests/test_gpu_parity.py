@@ -245,12 +245,48 @@ def test_kernel_variants_agree_bit_for_bit(pow_mode):
 def test_chunked_sweeps_are_bitwise_identical(chunks):
     """Bands of a sweep run as independent kernel chains on separate streams: same bits as one kernel per stage."""
     p, case = synthetic_case(1024, 300, seed=8)
-    a, b = solver_for(case, chunks=1), solver_for(case, chunks=chunks)
+    a, b = solver_for(case, chunks=1, fuse=0), solver_for(case, chunks=chunks, fuse=0)
     a.evolve(5)
     b.evolve(5)
     assert np.array_equal(a.download(STATE)[:, 2:-2, :], b.download(STATE)[:, 2:-2, :])
     assert np.array_equal(interior(a.download(TMP)), interior(b.download(TMP)))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("pow_mode", ["libdevice", "background"])
+@pytest.mark.parametrize("nx,nz,steps,tune", [
+    (100, 50, 4, {}),                              # BASELINE config 1 shape: ragged strips and tiles
+    (64, 16, 3, dict(sweep_lz=8)),                 # two z segments of 8 rows, one x tile
+    (250, 130, 3, dict(sweep_lz=37, sweep_xp=3)),  # ragged segments, three-pass x tiles
+    (1000, 333, 3, dict(sweep_lz=64)),
+    (2048, 256, 4, {}),
+    (236, 40, 2, dict(sweep_lz=8)),                # nx = 2 full x tiles exactly (rem == tile)
+    (238, 40, 2, dict(sweep_lz=13)),               # ... plus a 2-cell remainder tile
+])
+def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode):
+    """One kernel per directional sweep (T1, T2 on chip, 6-cell halo recomputed) against one kernel
+    per RK stage: identical bits for the state (interior and x halo images) and for state_tmp."""
+    p, case = synthetic_case(nx, nz, seed=nx + nz)
+    a, b = solver_for(case, "tma", pow_mode, fuse=0), solver_for(case, "tma", pow_mode, fuse=1, **tune)
+    for n in (1, steps):  # an odd and a longer call: both sweep orders, tmp written by the last sweep only
+        a.evolve(n)
+        b.evolve(n)
+        ra, rb = a.download(STATE), b.download(STATE)
+        assert np.array_equal(ra[:, 2:-2, :], rb[:, 2:-2, :])
+        assert np.array_equal(interior(a.download(TMP)), interior(b.download(TMP)))
+    assert b.launch_count < a.launch_count
+    a.close(); b.close()
+
+
+def test_fused_sweeps_thermal_walls_vs_oracle():
+    """Thermal bubble 100x50 x 100 steps through the fused sweeps against the golden reference state."""
+    g = golden("evolve_thermal_100x50.npz")
+    p, case = case_from_golden(g, "state0")
+    s = solver_for(case, fuse=1, sweep_lz=16)
+    s.evolve(100)
+    assert worst_rel_l2(s.download(STATE), g["state_100"]) <= STATE_TOL
+    assert_stats(s.stats(STATE), g["stats_100"])
+    s.close()
 
 
 def test_mass_conservation_and_variant_agreement_full_size():
