@@ -120,11 +120,12 @@ def load():
     """Return the loaded library (cached).  Raises if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("PMW_LIB", LIB_PATH)  # development: an alternative build of the same library
+        if not os.path.exists(path):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback for the pyminiweather_b200 operators)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype = res

@@ -75,7 +75,7 @@ struct pmw_ctx {
     bool xhalo_valid[3];  // x halo columns hold the periodic image of the interior
     bool xhalo6_valid[3];  // ... and so do the four further columns a fused x sweep reads (6-wide image)
     // fused sweeps (pmw_sweep.cuh): 1 = pmw_evolve runs one kernel per directional sweep
-    int fuse, keep_tmp, sweep_lz, sweep_xp;
+    int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt;
     double* hydro_blob;
     double* src_w;  // gravity-wave forcing field or nullptr
     Hydro hy;
@@ -193,6 +193,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->keep_tmp = 1;
     c->sweep_lz = 0;  // 0 = choose from the grid (pick_sweep_lz)
     c->sweep_xp = 2;
+    c->sweep_zt = 0;  // z sweeps: 0 = streaming kernel (72 us at 2048x1024), 1 = transposing x-style kernel (90 us)
     c->l2p[PMW_BUF_STATE] = 0;
     c->l2p[PMW_BUF_TMP] = 1;
     c->spare = 2;
@@ -303,6 +304,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
     } else if (!strcmp(key, "sweep_lz")) {
         NEED(value == 0 || value >= 8, "sweep_lz must be 0 (automatic) or >= 8");
         c->sweep_lz = value;
+    } else if (!strcmp(key, "sweep_zt")) {
+        c->sweep_zt = value ? 1 : 0;
     } else if (!strcmp(key, "sweep_xp")) {
         NEED(value == 2 || value == 3, "sweep_xp must be 2 or 3");
         c->sweep_xp = value;
@@ -325,6 +328,7 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     else if (!strcmp(key, "keep_tmp")) *value = c->keep_tmp;
     else if (!strcmp(key, "sweep_lz")) *value = c->sweep_lz;
     else if (!strcmp(key, "sweep_xp")) *value = c->sweep_xp;
+    else if (!strcmp(key, "sweep_zt")) *value = c->sweep_zt;
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
 }
@@ -1010,17 +1014,32 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         }
         const int P = c->sweep_xp;
         const int LC = 64 * P - 10;
-        if ((rc = get_tmap(c, pS, 64 * P + 4, 4, &tm, true)) != PMW_OK) return rc;
-        const dim3 grid((c->p.nx + LC - 1) / LC, (c->p.nz + 3) / 4 + (a.push_epoch ? 1 : 0));
+        if ((rc = get_tmap(c, pS, 64 * P + 4, 1, &tm, true)) != PMW_OK) return rc;
+        const int ntx = (c->p.nx + LC - 1) / LC;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
+        // persistent: every warp walks its own list of (row, tile) items; as many CTAs of 4 warps as
+        // are resident at once
+        const long long nitems = (long long)c->p.nz * ntx;
 #define GO(PP, PM, WT)                                                                                  \
     do {                                                                                                \
-        using T = XSweepTile<4, PP>;                                                                    \
+        using T = XSweepTile<PP>;                                                                       \
         static unsigned long long attr_done = 0;                                                        \
+        static int per_sm[64];                                                                          \
         if (!(attr_done >> c->p.device & 1ull)) {                                                       \
-            if ((rc = set_smem(sweep_x<4, PP, PM, WT>, T::smem_bytes())) != PMW_OK) return rc;          \
+            if ((rc = set_smem(sweep_x<PP, PM, WT>, T::smem_bytes())) != PMW_OK) return rc;             \
+            int nb = 0;                                                                                 \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_x<PP, PM, WT>, 32 * T::WARPS, \
+                                                                 T::smem_bytes()));                     \
+            per_sm[c->p.device & 63] = std::max(nb, 1);                                                 \
             attr_done |= 1ull << c->p.device;                                                           \
         }                                                                                               \
-        launch_ex(sweep_x<4, PP, PM, WT>, grid, dim3(T::THREADS), T::smem_bytes(), c->stream, c->pdl != 0, *tm, a); \
+        const int ncta = (int)std::min<long long>((long long)nsm * per_sm[c->p.device & 63],            \
+                                                  (nitems + T::WARPS - 1) / T::WARPS);                  \
+        const int npush = a.push_epoch ? std::min(ncta, 8) : 0;                                         \
+        const dim3 grid(ncta);                                                                          \
+        launch_ex(sweep_x<PP, PM, WT>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl != 0, *tm, a, \
+                  ntx, npush);                                                                          \
     } while (0)
 #define GO_P(PM, WT) do { if (P == 2) GO(2, PM, WT); else GO(3, PM, WT); } while (0)
         if (fast) { if (write_tmp) GO_P(1, true); else GO_P(1, false); }
@@ -1028,6 +1047,35 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
 #undef GO_P
 #undef GO
         LAUNCHED(c, "sweep_x");
+    } else if (c->sweep_zt) {
+        // transposing z sweep: items = (group of 4 columns, z tile); as many CTAs as are resident at once
+        const int P = 2, LC = 64 * P - 10;
+        if ((rc = get_tmap(c, pS, 4, 64 * P + 4, &tm, true)) != PMW_OK) return rc;
+        const int ngroups = (c->p.nx + 3) / 4, ntz = (c->p.nz + LC - 1) / LC;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
+#define GO(PM, WT)                                                                                      \
+    do {                                                                                                \
+        using T = ZTSweepTile<2>;                                                                       \
+        static unsigned long long attr_done = 0;                                                        \
+        static int per_sm[64];                                                                          \
+        if (!(attr_done >> c->p.device & 1ull)) {                                                       \
+            if ((rc = set_smem(sweep_zt<2, PM, WT>, T::smem_bytes())) != PMW_OK) return rc;             \
+            int nb = 0;                                                                                 \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_zt<2, PM, WT>, 32 * T::WARPS, \
+                                                                 T::smem_bytes()));                     \
+            per_sm[c->p.device & 63] = std::max(nb, 1);                                                 \
+            attr_done |= 1ull << c->p.device;                                                           \
+        }                                                                                               \
+        const int ncta = (int)std::min<long long>((long long)nsm * per_sm[c->p.device & 63],            \
+                                                  (long long)ngroups * ntz);                            \
+        launch_ex(sweep_zt<2, PM, WT>, dim3(ncta), dim3(32 * T::WARPS), T::smem_bytes(), c->stream,     \
+                  c->pdl != 0, *tm, a, ngroups, ntz);                                                   \
+    } while (0)
+        if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
+        else      { if (write_tmp) GO(0, true); else GO(0, false); }
+#undef GO
+        LAUNCHED(c, "sweep_zt");
     } else {
         a.lz = pick_sweep_lz(c);
         if ((rc = get_tmap(c, pS, ZS_COLS, 1, &tm, true)) != PMW_OK) return rc;
@@ -1070,6 +1118,7 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
         const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
         for (int d = 0; d < 2; ++d) {
             int rc = PMW_OK;
+            if (fused && (c->peer_dbg & (dirs[d] == PMW_DIR_X ? 16 : 8))) continue;  // development: time one direction
             if (fused) {
                 // state_tmp (the reference's stage-2 array) is only materialised by the last sweep of the call
                 rc = evolve_sweep_fused(c, dirs[d], dt, c->keep_tmp && n == nsteps - 1 && d == 1);

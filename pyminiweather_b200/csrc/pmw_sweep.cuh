@@ -62,12 +62,12 @@ struct SweepArgs {
 
 // Slab ring, fused x sweep: the first row of CTAs stores this slab's own six edge columns of S
 // into the neighbours' halo columns and publishes push_epoch (cf. push_halo_role).
-__device__ __forceinline__ void push_halo6_role(const SweepArgs& a)
+__device__ __forceinline__ void push_halo6_role(const SweepArgs& a, int npush)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const Layout& L = a.L;
     const int per_row = SWEEP_HALO / 2;  // column pairs per side
-    for (int t = blockIdx.x * nthr + tid; t < NVAR * L.nz * per_row; t += gridDim.x * nthr) {
+    for (int t = blockIdx.x * nthr + tid; t < NVAR * L.nz * per_row; t += npush * nthr) {
         const int j = t % per_row, k = (t / per_row) % L.nz, v = t / (per_row * L.nz);
         const double2 first = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, HS + 2 * j));
         const double2 last =
@@ -78,7 +78,7 @@ __device__ __forceinline__ void push_halo6_role(const SweepArgs& a)
     }
     __threadfence_system();
     __syncthreads();
-    if (tid == 0 && atomicAdd(a.push_counter, 1u) == gridDim.x - 1) {
+    if (tid == 0 && atomicAdd(a.push_counter, 1u) == (unsigned)npush - 1) {
         *a.push_counter = 0;
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.nbr_flags_left + 1), "l"(a.push_epoch) : "memory");
@@ -88,14 +88,28 @@ __device__ __forceinline__ void push_halo6_role(const SweepArgs& a)
 
 // ------------------------------------------------------------------------------------------
 // x sweep
+//   Work item = one interior row k x one column tile of LC = 64P-10 owned cells (tile column t holds
+//   interior column c0-6+t, FW = 64P+4 tile columns).  Persistent kernel: every WARP walks its own
+//   list of items (grid-stride) and never synchronises with another warp.  Per warp, in shared
+//   memory: two state rows S[2][4][FW] -- the row of the next item is in flight (one TMA box, own
+//   mbarrier) while the current one is computed -- and one row T[4][FW+2] for the intermediate
+//   states: stage 1 writes T1 there, stage 2 overwrites it IN PLACE with T2 shifted two columns
+//   to the right (the warp walks right to left, so a pass only overwrites columns no later pass
+//   reads), stage 3 reads T2 at the shifted position and stores the owned cells to HBM.
 // ------------------------------------------------------------------------------------------
-template <int TR, int P>
+template <int P>
 struct XSweepTile {
     static constexpr int FW = 64 * P + 4;   // tile columns (state box width)
     static constexpr int LC = 64 * P - 10;  // owned cells per row
-    static constexpr int ELEMS = NVAR * TR * FW;
-    static constexpr int THREADS = 32 * TR;
-    static constexpr size_t smem_bytes() { return (size_t)3 * ELEMS * sizeof(double) + 16; }
+    static constexpr int TW = FW + 2;       // T row: two extra columns for the shifted T2
+#ifndef PMW_XSWEEP_WARPS
+#define PMW_XSWEEP_WARPS 4
+#endif
+    static constexpr int WARPS = PMW_XSWEEP_WARPS;  // per CTA (no block-level synchronisation: any number works)
+    static constexpr int S_ELEMS = NVAR * FW;
+    static constexpr int T_ELEMS = (NVAR * TW + 15) / 16 * 16;
+    static constexpr int WARP_ELEMS = 2 * S_ELEMS + T_ELEMS;
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16); }
 };
 
 // Both interface fluxes of a lane's pair with ONE warp-uniform fallback branch (see
@@ -127,147 +141,384 @@ __device__ __forceinline__ void xpair_flux(const double (&t0)[4], const double (
     }
 }
 
-// The three stages and the passes of a stage run through ONE copy of the pass body (runtime loops):
-// the whole kernel stays inside the instruction cache.  Tile column t holds interior column c0-6+t.
-template <int TR, int P, int POW_MODE, bool WRITE_TMP>
-__global__ void __launch_bounds__(32 * TR, (P == 2 && TR == 4) ? 4 : 1)
-sweep_x(const __grid_constant__ CUtensorMap tm_state, const SweepArgs a)
+struct XItem {
+    int k, c0, tx;
+};
+// Items are numbered tile column by tile column (rows fastest); in a slab ring the two edge columns,
+// whose halo cells arrive from the neighbours over NVLink, come last.
+__device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int edge_last)
 {
-    using T = XSweepTile<TR, P>;
-    constexpr int VS = TR * T::FW;
+    XItem it;
+    const int cidx = n / nz;
+    it.k = n - cidx * nz;
+    it.tx = !edge_last ? cidx : ((cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1));
+    it.c0 = it.tx * lc;
+    return it;
+}
+
+#ifndef PMW_XSWEEP_MINB
+#define PMW_XSWEEP_MINB 3
+#endif
+template <int P, int POW_MODE, bool WRITE_TMP>
+#ifdef PMW_XSWEEP_MAXNREG
+__global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
+#else
+__global__ void __launch_bounds__(32 * XSweepTile<P>::WARPS, PMW_XSWEEP_MINB)
+#endif
+sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int ntx, const int npush)
+{
+    using T = XSweepTile<P>;
+    constexpr int FW = T::FW, TW = T::TW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sS = reinterpret_cast<double*>(smem_raw);
-    double* sT1 = sS + T::ELEMS;
-    double* sT2 = sT1 + T::ELEMS;
-    static_assert((T::ELEMS * 8) % 128 == 0, "tiles stay 128-byte aligned");
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + T::ELEMS);
-
-    const int ntx = gridDim.x;
-    const int push_rows = a.push_epoch ? 1 : 0;
-    const int nty = gridDim.y - push_rows;
-    if (push_rows && blockIdx.y == 0) {
-        pdl_launch_dependents();
-        pdl_wait();
-        push_halo6_role(a);
-        return;
-    }
-    int tx = blockIdx.x, ty = blockIdx.y - push_rows;
-    if (a.edge_last) {  // slab ring: the tile columns that read neighbour halos are the last CTAs
-        const int lin = ty * ntx + tx;
-        const int cidx = lin / nty;
-        ty = lin % nty;
-        tx = (cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1);
-    }
-    ty += a.tile_y0;
-    const int nx = a.L.nx, nz = a.L.nz;
-    const int c0 = tx * T::LC;  // first owned interior column (even)
-    const int r0 = ty * TR;
-    pdl_launch_dependents();
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm_state);
-        mbar_init(bar, 1);
-    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // columns of T1 / T2 that no stage writes but the next stage's (discarded) edge interfaces read
-    {
-        double* r1 = sT1 + warp * T::FW;
-        double* r2 = sT2 + warp * T::FW;
-        if (lane < 16) {
-            const int v = lane >> 2, j = lane & 3;
-            if (j < 2) r1[v * VS + j] = 0.0;
-            r1[v * VS + 64 * P + j] = 0.0;
-            r2[v * VS + j] = 0.0;
-            r2[v * VS + 64 * P + j] = 0.0;
-            if (j < 2) r2[v * VS + 64 * P - 2 + j] = 0.0;
-        }
-    }
-    __syncthreads();
-    pdl_wait();  // everything below reads state produced by the previous kernel
-    if (threadIdx.x == 0) {
-        if (a.wait_epoch && !(a.dbg & 2)) {
-            if (c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
-            if (c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
-        }
-        mbar_arrive_expect_tx(bar, (uint32_t)(T::ELEMS * sizeof(double)));
-        // map column 0 is interior column -6 (array column -4)
-        tma_load_3d(sS, &tm_state, c0, r0 + HS, 0, bar, l2_policy(1));
-    }
-    const int k = r0 + warp;
-    const bool row_ok = k < nz;
-    const int kc = min(k, nz - 1);
-    const IfaceBg bg = bg_x(a.hy, kc + HS);
-    // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
-    // q only matters while 64q <= that limit (warp-uniform)
-    const int rem = min(nx - c0, T::LC);
-    const double* rowS = sS + warp * T::FW + 2 * lane;
-    double* const po = a.out + idx(a.L, 0, kc + HS, c0 - SWEEP_HALO + HS + 2 * lane);
-    double* const pt = a.tmp + idx(a.L, 0, kc + HS, c0 - SWEEP_HALO + HS + 2 * lane);
-    const int src_lane = (lane + 1) & 31;
-    const int i0 = c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
-    mbar_wait(bar, 0);
+    double* const sS = reinterpret_cast<double*>(smem_raw) + warp * T::WARP_ELEMS;
+    double* const sT = sS + 2 * T::S_ELEMS;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS) + 2 * warp;
+    static_assert((T::S_ELEMS * 8) % 128 == 0 && (T::WARP_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
 
-    const double* src = rowS;
-    double* dst = sT1 + warp * T::FW + 2 * lane;
-    double dts = a.dt1;
-    int tlo = 2, thi = 64 * P;
+    const int nx = a.L.nx, nz = a.L.nz;
+    const int nitems = nz * ntx;
+    const int nwarps = gridDim.x * T::WARPS;
+    const int w = blockIdx.x * T::WARPS + warp;
+    pdl_launch_dependents();
+    if (lane == 0) {
+        tma_prefetch_desc(&tm_row);
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+    }
+    // columns of T no stage writes (zero: they only feed interfaces whose results are discarded)
+    for (int e = lane; e < NVAR * 8; e += 32) {
+        const int v = e >> 3, j = e & 7;
+        sT[v * TW + (j < 2 ? j : 64 * P - 2 + j)] = 0.0;  // tile columns 0, 1 and 64P .. 64P+5
+    }
+    __syncwarp();
+    pdl_wait();  // everything below reads state produced by the previous kernel
+    if (a.push_epoch && blockIdx.x < npush) push_halo6_role(a, npush);
+
+    const unsigned long long pol = l2_policy(1);
+    auto request = [&](int n, int buf) {  // lane 0: start the load of item n's state row
+        const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
+        if (a.wait_epoch && !(a.dbg & 2)) {
+            if (it.c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
+            if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old row before the TMA write
+        mbar_arrive_expect_tx(bars + buf, (uint32_t)(T::S_ELEMS * sizeof(double)));
+        // map column 0 is interior column -6 (array column -4)
+        tma_load_3d(sS + buf * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
+    };
+    if (w < nitems && lane == 0) request(w, 0);
+    const int src_lane = (lane + 1) & 31;
+    int buf = 0;
+    unsigned phase = 0;  // bit b: parity of the next completion of bars[b]
 #pragma unroll 1
-    for (int s = 0; s < 3; ++s) {
-        const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
-        double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
+    for (int n = w; n < nitems; n += nwarps) {
+        const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
+        if (n + nwarps < nitems && lane == 0) request(n + nwarps, buf ^ 1);
+        const IfaceBg bg = bg_x(a.hy, it.k + HS);
+        // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
+        // q only matters while 64q <= that limit (warp-uniform)
+        const int rem = min(nx - it.c0, T::LC);
+        const double* const rowS = sS + buf * T::S_ELEMS + 2 * lane;
+        double* const rowT = sT + 2 * lane;
+        double* const po = a.out + idx(a.L, 0, it.k + HS, it.c0 - SWEEP_HALO + HS + 2 * lane);
+        const long long tmp_off = a.tmp - a.out;
+        const int i0 = it.c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
+        mbar_wait(bars + buf, (phase >> buf) & 1);
+        phase ^= 1u << buf;
+
+        const double* src = rowS;  // forcing row of the stage (+ 2*lane)
+        int vs = FW;               // its plane stride
+        double dts = a.dt1;
+        int tlo = 2, thi = 64 * P;
 #pragma unroll 1
-        for (int q = nq - 1; q >= 0; --q) {
-            double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
+        for (int s = 0; s < 3; ++s) {
+            const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
+            double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const double* p = src + v * VS + 64 * q;
-                const Pair u01 = lds2(p), u23 = lds2(p + 2);
-                t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
-            }
-            xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
-            const int t = 64 * q + 2 * lane + 2;  // tile column of the left cell of the pair
-            const int i = i0 + 64 * q;
-            bool ok = t >= tlo && t < thi;
-            if (s == 2) ok = ok && row_ok && i < nx;
-            double xa[4], xb[4];
+            for (int q = P - 1; q >= 0; --q) {
+                if (q >= nq) continue;
+                double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const double give = (lane == 0) ? keep[v] : f0[v];
-                const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
-                keep[v] = f0[v];
-                double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
-                if (s != 0) {
-                    const Pair in = lds2(rowS + v * VS + 64 * q + 2);
-                    ia = in.a; ib = in.b;
+                for (int v = 0; v < 4; ++v) {
+                    const double* p = src + v * vs + 64 * q;
+                    const Pair u01 = lds2(p), u23 = lds2(p + 2);
+                    t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
                 }
-                const double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
-                xa[v] = fma(dts, ta, ia);
-                xb[v] = fma(dts, tb, ib);
-            }
-            if (ok) {
-                if (s != 2) {
+                xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
+                const int t = 64 * q + 2 * lane + 2;  // tile column of the left cell of the pair
+                const int i = i0 + 64 * q;
+                bool ok = t >= tlo && t < thi;
+                if (s == 2) ok = ok && i < nx;
+                // stage 1 -> T1 at column t, stage 2 -> T2 at column t+2 (in place), stage 3 -> HBM
+                double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + 64 * q + 2 + 2 * s;
+                const long long dvs = (s == 2) ? a.L.vstride : (long long)TW;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v)
-                        *reinterpret_cast<double2*>(dst + v * VS + 64 * q + 2) = make_double2(xa[v], xb[v]);
-                } else {
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const long long o = v * a.L.vstride + 64 * q + 2;
-                        *reinterpret_cast<double2*>(po + o) = make_double2(xa[v], xb[v]);
+                for (int v = 0; v < 4; ++v) {
+                    const double give = (lane == 0) ? keep[v] : f0[v];
+                    const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
+                    keep[v] = f0[v];
+                    double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
+                    if (s != 0) {
+                        const Pair in = lds2(rowS + v * FW + 64 * q + 2);
+                        ia = in.a; ib = in.b;
+                    }
+                    const double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                    const double2 x = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
+                    if (ok) *reinterpret_cast<double2*>(dst + v * dvs) = x;  // generic store: shared or global
+                    if (s == 2 && ok) {
                         if (a.periodic) {
-                            if (i < SWEEP_HALO) *reinterpret_cast<double2*>(po + o + nx) = make_double2(xa[v], xb[v]);
-                            if (i >= nx - SWEEP_HALO) *reinterpret_cast<double2*>(po + o - nx) = make_double2(xa[v], xb[v]);
+                            if (i < SWEEP_HALO) *reinterpret_cast<double2*>(dst + v * dvs + nx) = x;
+                            if (i >= nx - SWEEP_HALO) *reinterpret_cast<double2*>(dst + v * dvs - nx) = x;
                         }
-                        if (WRITE_TMP) *reinterpret_cast<double2*>(pt + o) = make_double2(t2[v], t3[v]);
+                        if (WRITE_TMP) *reinterpret_cast<double2*>(dst + v * dvs + tmp_off) = make_double2(t2[v], t3[v]);
                     }
                 }
             }
+            __syncwarp();
+            src = rowT + 2 * s;  // T1 at its own columns, T2 shifted by two
+            vs = TW;
+            dts = (s == 0) ? a.dt2 : a.dt3;
+            tlo += 2;
+            thi -= 2;
         }
-        __syncwarp();
-        src = (s == 0) ? sT1 + warp * T::FW + 2 * lane : sT2 + warp * T::FW + 2 * lane;
-        dst = sT2 + warp * T::FW + 2 * lane;
-        dts = (s == 0) ? a.dt2 : a.dt3;
-        tlo += 2;
-        thi -= 2;
+        buf ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// z sweep, transposing variant (sweep_zt): the x-sweep organisation applied along z.
+//   The state stays x-fastest in HBM.  Work item = a group of 4 adjacent columns x one z tile of
+//   LC = 64P-10 owned rows (+6 halo rows either side).  A CTA of 4 warps owns the item: one TMA
+//   box [4 vars][FW rows][4 columns] (32-byte row pieces) lands in a raw buffer; every warp copies
+//   ITS column out of it into a z-contiguous shared-memory row (the transposition), and from there
+//   on runs exactly the warp-autonomous three-stage pipeline of sweep_x along z: lanes own pairs
+//   of vertically adjacent cells, T1 / T2 live in one in-place row, fluxes travel by shuffle.
+//   Stage 3 deposits the new state in the (dead) raw buffer, [var][row][4 columns], and the CTA
+//   stores it as 32-byte row pieces.  The raw buffer is double-buffered: the next item's box is in
+//   flight during the current item.  Solid walls (set_bc_z, bcs.py:92-148): the two halo cells
+//   beyond a wall are rebuilt in the warp's row before each stage; rows outside the array arrive
+//   as zeros (TMA out-of-bounds fill) and only feed discarded interfaces.
+// ------------------------------------------------------------------------------------------
+template <int P>
+struct ZTSweepTile {
+    static constexpr int FW = 64 * P + 4;
+    static constexpr int LC = 64 * P - 10;
+    static constexpr int TW = FW + 2;
+    static constexpr int WARPS = 4;  // = columns per group
+    static constexpr int RAW_ELEMS = NVAR * FW * WARPS;
+    static constexpr int S_ELEMS = NVAR * FW;
+    static constexpr int T_ELEMS = (NVAR * TW + 15) / 16 * 16;
+    static constexpr int H_ELEMS = 4 * FW;  // hydrostatic interface profiles of the tile
+    static constexpr size_t smem_bytes()
+    {
+        return (size_t)(2 * RAW_ELEMS + WARPS * (S_ELEMS + T_ELEMS) + H_ELEMS) * sizeof(double) + 32;
+    }
+};
+
+// Rebuild the two cells beyond a wall in a forcing row (`row` = column 0 of variable 0, plane stride vs).
+__device__ __forceinline__ void zt_wall_fix(double* row, int vs, int r0, int nz, int fw, const double* hd, int lane)
+{
+    if (lane < 8) {
+        const int v = lane >> 1, j = lane & 1;
+        if (r0 == 0)  // cells -2, -1 are tile columns 4, 5; interior cell 0 is column 6
+            row[v * vs + 4 + j] = wall_value(v, row[v * vs + 6], __ldg(hd + HS), __ldg(hd + j));
+        const int tt = nz - r0 + SWEEP_HALO;  // tile column of cell nz
+        if (tt + 1 < fw)
+            row[v * vs + tt + j] = wall_value(v, row[v * vs + tt - 1], __ldg(hd + nz + HS - 1), __ldg(hd + nz + HS + j));
+    }
+    __syncwarp();
+}
+
+#ifndef PMW_ZTSWEEP_MINB
+#define PMW_ZTSWEEP_MINB 3
+#endif
+template <int P, int POW_MODE, bool WRITE_TMP>
+__global__ void __launch_bounds__(32 * ZTSweepTile<P>::WARPS, PMW_ZTSWEEP_MINB)
+sweep_zt(const __grid_constant__ CUtensorMap tm_box, const SweepArgs a, const int ngroups, const int ntz)
+{
+    using T = ZTSweepTile<P>;
+    constexpr int FW = T::FW, TW = T::TW, LC = T::LC, NW = T::WARPS;
+    constexpr int WSTRIDE = T::S_ELEMS + T::T_ELEMS;  // doubles between the rows of consecutive warps
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* const raw = reinterpret_cast<double*>(smem_raw);  // [2][4][FW][NW]
+    double* const rows = raw + 2 * T::RAW_ELEMS;              // [NW]{ S[4][FW], T[4][TW] }
+    double* const sS = rows + warp * WSTRIDE;
+    double* const sT = sS + T::S_ELEMS;
+    double* const sH = rows + NW * WSTRIDE;  // [4][FW]: dens, dens_theta, 1/dens_theta, pressure per tile interface
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sH + T::H_ELEMS);
+    static_assert((T::RAW_ELEMS * 8) % 128 == 0, "raw boxes stay 128-byte aligned");
+
+    const int nx = a.L.nx, nz = a.L.nz;
+    const int nitems = ngroups * ntz;
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_box);
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+    }
+    for (int e = lane; e < NVAR * 8; e += 32) {  // columns of T no stage writes
+        const int v = e >> 3, j = e & 7;
+        sT[v * TW + (j < 2 ? j : 64 * P - 2 + j)] = 0.0;
+    }
+    __syncthreads();
+    pdl_wait();
+    const unsigned long long pol = l2_policy(1);
+    auto request = [&](int n, int buf) {  // thread 0: start the load of item n's box
+        const int g = n % ngroups, tz = n / ngroups;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old box before the TMA write
+        mbar_arrive_expect_tx(bars + buf, (uint32_t)(T::RAW_ELEMS * sizeof(double)));
+        // map column = array column + 4 = interior column + 6; array row = cell row + 2 (may be negative: zero fill)
+        tma_load_3d(raw + buf * T::RAW_ELEMS, &tm_box, NW * g + SWEEP_HALO, tz * LC - SWEEP_HALO + HS, 0, bars + buf, pol);
+    };
+    if (blockIdx.x < nitems && threadIdx.x == 0) request(blockIdx.x, 0);
+    const int src_lane = (lane + 1) & 31;
+    const double* const hd = a.hy.dens_cell;
+    int buf = 0, tz_loaded = -1;
+    unsigned phase = 0;
+#pragma unroll 1
+    for (int n = blockIdx.x; n < nitems; n += gridDim.x) {
+        const int g = n % ngroups, tz = n / ngroups;
+        if (threadIdx.x == 0 && n + (int)gridDim.x < nitems) request(n + gridDim.x, buf ^ 1);
+        const int r0 = tz * LC;  // first owned cell row
+        if (tz != tz_loaded) {   // interface profiles of this z tile: tile column j is interface r0 - 4 + j
+            for (int j = threadIdx.x; j < FW; j += 32 * NW) {
+                const int kc = min(max(r0 - 4 + j, 0), nz);
+                sH[j] = __ldg(a.hy.dens_int + kc);
+                sH[FW + j] = __ldg(a.hy.dens_theta_int + kc);
+                sH[2 * FW + j] = __ldg(a.hy.inv_dens_theta_int + kc);
+                sH[3 * FW + j] = __ldg(a.hy.pressure_int + kc);
+            }
+            tz_loaded = tz;
+        }
+        const double* const box = raw + buf * T::RAW_ELEMS;
+        mbar_wait(bars + buf, (phase >> buf) & 1);
+        phase ^= 1u << buf;
+        // transposition: every thread takes whole 32-byte rows of the box and deals the four columns
+        // out to the four warps' z-contiguous rows
+        for (int e = threadIdx.x; e < NVAR * FW; e += 32 * NW) {
+            const double2 c01 = *reinterpret_cast<const double2*>(box + e * NW);
+            const double2 c23 = *reinterpret_cast<const double2*>(box + e * NW + 2);
+            rows[e] = c01.x;
+            rows[WSTRIDE + e] = c01.y;
+            rows[2 * WSTRIDE + e] = c23.x;
+            rows[3 * WSTRIDE + e] = c23.y;
+        }
+        __syncthreads();  // (A) rows and profiles complete; the box is dead
+        zt_wall_fix(sS, FW, r0, nz, FW, hd, lane);
+
+        const int rem = min(nz - r0, LC);
+        double* const rowS = sS + 2 * lane;
+        double* const rowT = sT + 2 * lane;
+        const double* src = rowS;
+        int vs = FW;
+        double dts = a.dt1;
+        int tlo = 2, thi = 64 * P;
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+            const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
+            double keep[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = P - 1; q >= 0; --q) {
+                if (q >= nq) continue;
+                double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const double* p = src + v * vs + 64 * q;
+                    const Pair u01 = lds2(p), u23 = lds2(p + 2);
+                    t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
+                }
+                // interface index of tile column j is r0 - 4 + j; the pair's left cell has the same index
+                const int j0 = 64 * q + 2 * lane;
+                const int k0 = r0 - 4 + j0;
+                IfaceBg bg0, bg1;
+                {
+                    const Pair d = lds2(sH + j0), dt = lds2(sH + FW + j0), idt = lds2(sH + 2 * FW + j0),
+                               pr = lds2(sH + 3 * FW + j0);
+                    bg0.dens = d.a; bg0.dens_theta = dt.a; bg0.inv_dens_theta = idt.a; bg0.pressure = pr.a;
+                    bg1.dens = d.b; bg1.dens_theta = dt.b; bg1.inv_dens_theta = idt.b; bg1.pressure = pr.b;
+                }
+                const bool w0 = (k0 == 0 || k0 == nz), w1 = (k0 + 1 == 0 || k0 + 1 == nz);
+                const bool bad0 = interface_flux_fast<true, POW_MODE>(t0, t1, t2, t3, bg0, a.hv_coeff, w0, f0);
+                const bool bad1 = interface_flux_fast<true, POW_MODE>(t1, t2, t3, t4, bg1, a.hv_coeff, w1, f1);
+                if (__any_sync(0xffffffffu, bad0 || bad1)) {
+                    asm volatile("" ::: "memory");
+                    Taps TT;
+                    if (bad0) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) { TT.s[0][v] = t0[v]; TT.s[1][v] = t1[v]; TT.s[2][v] = t2[v]; TT.s[3][v] = t3[v]; }
+                        const Flux4 gg = interface_flux_slow<true, POW_MODE>(TT, bg0, a.hv_coeff, w0);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) f0[v] = gg.f[v];
+                    }
+                    if (bad1) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) { TT.s[0][v] = t1[v]; TT.s[1][v] = t2[v]; TT.s[2][v] = t3[v]; TT.s[3][v] = t4[v]; }
+                        const Flux4 gg = interface_flux_slow<true, POW_MODE>(TT, bg1, a.hv_coeff, w1);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) f1[v] = gg.f[v];
+                    }
+                }
+                const int t = j0 + 2;  // tile column of the pair's left cell (cell row k0)
+                const bool ok = t >= tlo && t < thi && k0 >= 0 && k0 < nz;
+                // stage 1 -> T1 at column t, stage 2 -> T2 at column t+2 (in place), stage 3 -> over S at column
+                // t: the lane has read its initial state there and stage 3 reads no other column of S
+                double* const dst = (s == 2) ? rowS + 64 * q + 2 : rowT + 64 * q + 2 + 2 * s;
+                const int dvs = (s == 2) ? FW : TW;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const double give = (lane == 0) ? keep[v] : f0[v];
+                    const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's top face
+                    keep[v] = f0[v];
+                    double ia = t2[v], ib = t3[v];
+                    if (s != 0) {
+                        const Pair in = lds2(rowS + v * FW + 64 * q + 2);
+                        ia = in.a; ib = in.b;
+                    }
+                    double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                    if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250): the cells are taps 2 and 3
+                        ta = fma(-t2[DENS], GRAV, ta);
+                        tb = fma(-t3[DENS], GRAV, tb);
+                    }
+                    if (ok) *reinterpret_cast<double2*>(dst + v * dvs) = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
+                }
+            }
+            __syncwarp();
+            if (s < 2) zt_wall_fix(sT + 2 * s, TW, r0, nz, FW, hd, lane);
+            src = rowT + 2 * s;
+            vs = TW;
+            dts = (s == 0) ? a.dt2 : a.dt3;
+            tlo += 2;
+            thi -= 2;
+        }
+        __syncthreads();  // (B) the four columns of the new state are complete
+        if ((int)threadIdx.x < rem) {  // one owned row per thread: four columns = 32 bytes per variable
+            const int rr = threadIdx.x, i = NW * g;
+            double* const o = a.out + idx(a.L, 0, r0 + rr + HS, i + HS);
+            const long long tmp_off = a.tmp - a.out;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const double* c = rows + v * FW + SWEEP_HALO + rr;
+                const double2 x01 = make_double2(c[0], c[WSTRIDE]), x23 = make_double2(c[2 * WSTRIDE], c[3 * WSTRIDE]);
+                double* ov = o + v * a.L.vstride;
+                *reinterpret_cast<double2*>(ov) = x01;
+                if (i + 2 < nx) *reinterpret_cast<double2*>(ov + 2) = x23;
+                if (a.periodic) {
+                    if (i < SWEEP_HALO) *reinterpret_cast<double2*>(ov + nx) = x01;
+                    if (i + 2 < SWEEP_HALO) *reinterpret_cast<double2*>(ov + 2 + nx) = x23;
+                    if (i >= nx - SWEEP_HALO) *reinterpret_cast<double2*>(ov - nx) = x01;
+                    if (i + 2 >= nx - SWEEP_HALO && i + 2 < nx) *reinterpret_cast<double2*>(ov + 2 - nx) = x23;
+                }
+                if (WRITE_TMP) {  // T2 of the owned cells sits in the T rows, shifted by two columns
+                    const double* ct = rows + T::S_ELEMS + v * TW + SWEEP_HALO + 2 + rr;
+                    *reinterpret_cast<double2*>(ov + tmp_off) = make_double2(ct[0], ct[WSTRIDE]);
+                    if (i + 2 < nx) *reinterpret_cast<double2*>(ov + 2 + tmp_off) = make_double2(ct[2 * WSTRIDE], ct[3 * WSTRIDE]);
+                }
+            }
+        }
+        __syncthreads();  // (C) rows free for the next item
+        buf ^= 1;
     }
 }
 
@@ -406,15 +657,10 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
     if (zs.lane == 0) zs.request(j + 1 + ZS_AHEAD);
     zs.wait(j + 1);
     const double* top = zs.row(j + 1);
-    const double* r2 = zs.row(j - 4);
-    const double* r3 = zs.row(j - 7);
-    double in2[4], in3[4], f1[4], f2[4], f3[4], c1[4], c2[4], c3[4];
+    double f1[4], f2[4], f3[4], c1[4], c2[4], c3[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < 4; ++v)
         s1.W[R & 3][v] = top[v * ZS_COLS];  // newest state row replaces the oldest: taps now start at slot R+1
-        in2[v] = r2[v * ZS_COLS];
-        in3[v] = r3[v * ZS_COLS];
-    }
     const IfaceBg bg1 = bg_z(a.hy, j), bg2 = bg_z(a.hy, j - 3), bg3 = bg_z(a.hy, j - 6);
     const bool bad3 = s3.template flux_fast<R>(a, bg3, f3);
     const bool bad2 = s2.template flux_fast<R>(a, bg2, f2);
@@ -424,6 +670,16 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
         if (bad3) s3.template flux_slow<R>(a, bg3, f3);
         if (bad2) s2.template flux_slow<R>(a, bg2, f2);
         if (bad1) s1.template flux_slow<R + 1>(a, bg1, f1);
+    }
+    double in2[4], in3[4];  // initial state of the cells stages 2 and 3 finish (read late: short live ranges)
+    {
+        const double* r2 = zs.row(j - 4);
+        const double* r3 = zs.row(j - 7);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            in2[v] = r2[v * ZS_COLS];
+            in3[v] = r3[v * ZS_COLS];
+        }
     }
     if (WRITE_TMP && col_ok) {
 #pragma unroll

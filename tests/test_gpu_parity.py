@@ -258,16 +258,19 @@ def test_chunked_sweeps_are_bitwise_identical(chunks):
     (100, 50, 4, {}),                              # BASELINE config 1 shape: ragged strips and tiles
     (64, 16, 3, dict(sweep_lz=8)),                 # two z segments of 8 rows, one x tile
     (250, 130, 3, dict(sweep_lz=37, sweep_xp=3)),  # ragged segments, three-pass x tiles
-    (1000, 333, 3, dict(sweep_lz=64)),
+    (1000, 333, 3, dict(sweep_lz=64)),             # odd nz: a z tile ends on a single cell
+    (118, 119, 2, {}),                             # one x tile exactly; second z tile holds one row
+    (30, 236, 2, {}),                              # nx not a multiple of the 4-column groups; 2 full z tiles
     (2048, 256, 4, {}),
     (236, 40, 2, dict(sweep_lz=8)),                # nx = 2 full x tiles exactly (rem == tile)
     (238, 40, 2, dict(sweep_lz=13)),               # ... plus a 2-cell remainder tile
 ])
-def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode):
+@pytest.mark.parametrize("zt", [1, 0])
+def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode, zt):
     """One kernel per directional sweep (T1, T2 on chip, 6-cell halo recomputed) against one kernel
     per RK stage: identical bits for the state (interior and x halo images) and for state_tmp."""
     p, case = synthetic_case(nx, nz, seed=nx + nz)
-    a, b = solver_for(case, "tma", pow_mode, fuse=0), solver_for(case, "tma", pow_mode, fuse=1, **tune)
+    a, b = solver_for(case, "tma", pow_mode, fuse=0), solver_for(case, "tma", pow_mode, fuse=1, sweep_zt=zt, **tune)
     for n in (1, steps):  # an odd and a longer call: both sweep orders, tmp written by the last sweep only
         a.evolve(n)
         b.evolve(n)
@@ -278,11 +281,12 @@ def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode
     a.close(); b.close()
 
 
-def test_fused_sweeps_thermal_walls_vs_oracle():
+@pytest.mark.parametrize("zt", [1, 0])
+def test_fused_sweeps_thermal_walls_vs_oracle(zt):
     """Thermal bubble 100x50 x 100 steps through the fused sweeps against the golden reference state."""
     g = golden("evolve_thermal_100x50.npz")
     p, case = case_from_golden(g, "state0")
-    s = solver_for(case, fuse=1, sweep_lz=16)
+    s = solver_for(case, fuse=1, sweep_lz=16, sweep_zt=zt)
     s.evolve(100)
     assert worst_rel_l2(s.download(STATE), g["state_100"]) <= STATE_TOL
     assert_stats(s.stats(STATE), g["stats_100"])

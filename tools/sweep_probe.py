@@ -17,9 +17,8 @@ def run(**tune):
     t0 = time.perf_counter(); s.evolve(steps); s.synchronize(); dt = time.perf_counter() - t0
     s.close(); return dt / steps * 1e6, ref
 base = None
-cfgs = [dict(fuse=0), dict(fuse=1), dict(fuse=1, keep_tmp=0)]
-cfgs += [dict(fuse=1, sweep_lz=lz) for lz in (32, 43, 64, 86, 128)]
-cfgs += [dict(fuse=1, sweep_xp=3), dict(fuse=1, pdl=0)]
+cfgs = [dict(fuse=0), dict(fuse=1), dict(fuse=1, peer_dbg=8), dict(fuse=1, peer_dbg=16)]  # 8: x sweeps only, 16: z sweeps only
+cfgs += [dict(fuse=1, sweep_zt=0), dict(fuse=1, sweep_zt=0, peer_dbg=16), dict(fuse=1, pdl=0)]
 for tune in cfgs:
     try:
         us, st = run(**tune)
