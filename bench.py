@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one ``evolve()`` = 6 fused RK-stage kernels (3 z + 3 x) over the whole grid.
+One "step" = one ``evolve()`` = two fused sweep kernels (one per direction, three RK stages each;
+with ``--tune fuse=0``: six stage kernels) over the whole grid.
 Workload at N=1: BASELINE config 2, thermal rising bubble, nx=2048 nz=1024, fp64.  At N>1 the
 same slab (2048 x 1024 per GPU) is weak-scaled: global grid 2048*N x 1024, ring halo exchange
 before every x stage.  Metric: cell-updates/s = global cells * steps / time.
@@ -351,13 +352,18 @@ def run_gpu(args, rank, local_rank, world):
             traffic = _json.load(open(tpath)).get("dram_bytes_per_launch_mean")
         except Exception:
             pass
-    # One launch = one RK stage over the slab.  Algorithmic bytes per launch: stage 1
-    # 64 B/cell, stages 2-3 96 B/cell -> mean 512/6 B/cell.  Average launch duration = CUDA-event
-    # time of the timed region / stage launches in it (per rank; the only kernels a step launches
-    # are its six stage kernels, cf. profiles/*launch_list*): it includes the gaps between launches.
-    bytes_per_launch = NX_SLAB * NZ * BYTES_PER_CELL_STEP / STAGES_PER_STEP
-    launch_ms_region = ms / (args.steps * STAGES_PER_STEP)
+    # Launches per step: two sweep kernels (fused path) or six stage kernels.  Algorithmic bytes are
+    # SURVEY.md section 8d's stage-by-stage figure either way -- 64 + 96 + 96 = 256 B per cell per
+    # directional sweep, 512 B per cell-step -- so a fused sweep, which keeps T1/T2 on chip and moves
+    # only 64 B/cell, can exceed 1.0 of that roofline; `traffic` and `fused_*` show what it really
+    # moves and what bounds it (the FP64 pipe).  Average launch duration = CUDA-event time of the
+    # timed region / launches in it (per rank; the kernels a step launches are exactly these).
+    fused = bool(solver.get_tuning("fuse")) and args.variant == "tma"
+    launches_per_step = 2 if fused else STAGES_PER_STEP
+    bytes_per_launch = NX_SLAB * NZ * BYTES_PER_CELL_STEP / launches_per_step
+    launch_ms_region = ms / (args.steps * launches_per_step)
     achieved = bytes_per_launch / (launch_ms_region * 1e-3) / 1e9
+    fused_bytes_per_launch = NX_SLAB * NZ * 64.0  # state read once + written once per sweep
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -366,7 +372,7 @@ def run_gpu(args, rank, local_rank, world):
                                + ((" (BASELINE config 2)" if (NX_SLAB, NZ) == (2048, 1024) else "") if world == 1 else
                                   f" = {world} x-slabs of {NX_SLAB}x{NZ}, ring halo exchange per x stage ({args.halo})"),
                    "nx": NX_SLAB * world, "nz": NZ, "variant": args.variant, "pow_mode": args.pow_mode,
-                   "tiles": {k: solver.get_tuning(k) for k in ("x_tr", "x_p", "z_cfg")},
+                   "tiles": {k: solver.get_tuning(k) for k in ("fuse", "sweep_xp", "sweep_zt", "sweep_lz", "x_tr", "x_p", "z_cfg")},
                    "l2": f"no flush: working set = 3 state buffers x {4 * (NZ + 4) * (NX_SLAB + 4) * 8 / 1e6:.1f} MB "
                          "per GPU > 126 MB L2 (inputs larger than L2)",
                    "state_finite_after_run": finite,
@@ -377,10 +383,18 @@ def run_gpu(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src,
-                     "kernel": "stage_x_tma / stage_z_tma (one launch = one RK stage over the slab)",
+                     "kernel": ("sweep_x / sweep_z (one launch = one directional sweep = three RK stages over the slab)"
+                                if fused else "stage_x_tma / stage_z_tma (one launch = one RK stage over the slab)"),
                      "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "algorithmic_bytes_definition": "SURVEY 8d, stage by stage: 256 B per cell per sweep (512 B per cell-step)",
                      "launch_ms_mean": launch_ms_region,
-                     "launches_in_timed_region_per_rank": args.steps * STAGES_PER_STEP,
+                     "launches_in_timed_region_per_rank": args.steps * launches_per_step,
+                     "fused_min_bytes_per_launch": fused_bytes_per_launch if fused else None,
+                     "fused_hbm_frac": (fused_bytes_per_launch / (launch_ms_region * 1e-3) / 1e9 / peak) if fused else None,
+                     "note": ("fused sweeps move 64 B/cell per sweep instead of 256 and are bound by the FP64 pipe "
+                              "(profiles/: sm__inst_executed_pipe_fp64), so frac is measured against the "
+                              "stage-by-stage traffic the reference algorithm implies, not against what the kernel moves")
+                             if fused else None,
                      # second pass over the same K steps with an event pair around every stage kernel
                      # (serialises the launches: no programmatic dependent launch overlap)
                      "event_pair_launch_ms_mean": launch_ms, "event_pair_launches": n_timed,

@@ -940,7 +940,7 @@ static int evolve_sweep_chunked(pmw_ctx* c, int direction, double dt)
 static bool fuse_ok(const pmw_ctx* c)
 {
     return c->fuse && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && c->p.nx >= 16 && c->p.nz >= 8 &&
-           !c->src_w && !c->timing;
+           !c->src_w;
 }
 
 // Rows per z-sweep segment: a warp (32 columns x lz rows) is the unit of work and every SM holds
@@ -997,6 +997,17 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
     const CUtensorMap* tm = nullptr;
     int rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {  // pmw_stage_timing: an event pair around every sweep kernel
+        while (c->ev_used + 2 > c->ev.size()) {
+            cudaEvent_t e;
+            CU_TRY(cudaEventCreate(&e));
+            c->ev.push_back(e);
+        }
+        e0 = c->ev[c->ev_used];
+        e1 = c->ev[c->ev_used + 1];
+        c->ev_used += 2;
+    }
     if (direction == PMW_DIR_X) {
         if (c->peers) {
             a.push_epoch = a.wait_epoch = ++c->epoch;
@@ -1021,6 +1032,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         // persistent: every warp walks its own list of (row, tile) items; as many CTAs of 4 warps as
         // are resident at once
         const long long nitems = (long long)c->p.nz * ntx;
+        if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
 #define GO(PP, PM, WT)                                                                                  \
     do {                                                                                                \
         using T = XSweepTile<PP>;                                                                       \
@@ -1038,7 +1050,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
                                                   (nitems + T::WARPS - 1) / T::WARPS);                  \
         const int npush = a.push_epoch ? std::min(ncta, 8) : 0;                                         \
         const dim3 grid(ncta);                                                                          \
-        launch_ex(sweep_x<PP, PM, WT>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl != 0, *tm, a, \
+        launch_ex(sweep_x<PP, PM, WT>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a, \
                   ntx, npush);                                                                          \
     } while (0)
 #define GO_P(PM, WT) do { if (P == 2) GO(2, PM, WT); else GO(3, PM, WT); } while (0)
@@ -1054,6 +1066,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         const int ngroups = (c->p.nx + 3) / 4, ntz = (c->p.nz + LC - 1) / LC;
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
+        if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
 #define GO(PM, WT)                                                                                      \
     do {                                                                                                \
         using T = ZTSweepTile<2>;                                                                       \
@@ -1070,7 +1083,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         const int ncta = (int)std::min<long long>((long long)nsm * per_sm[c->p.device & 63],            \
                                                   (long long)ngroups * ntz);                            \
         launch_ex(sweep_zt<2, PM, WT>, dim3(ncta), dim3(32 * T::WARPS), T::smem_bytes(), c->stream,     \
-                  c->pdl != 0, *tm, a, ngroups, ntz);                                                   \
+                  c->pdl && !c->timing, *tm, a, ngroups, ntz);                                                   \
     } while (0)
         if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
         else      { if (write_tmp) GO(0, true); else GO(0, false); }
@@ -1080,12 +1093,14 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         a.lz = pick_sweep_lz(c);
         if ((rc = get_tmap(c, pS, ZS_COLS, 1, &tm, true)) != PMW_OK) return rc;
         const dim3 grid((c->p.nx + ZS_COLS - 1) / ZS_COLS, (c->p.nz + a.lz - 1) / a.lz);
-#define GO(PM, WT) launch_ex(sweep_z<PM, WT>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl != 0, *tm, a)
+        if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
+#define GO(PM, WT) launch_ex(sweep_z<PM, WT>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a)
         if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
         else      { if (write_tmp) GO(0, true); else GO(0, false); }
 #undef GO
         LAUNCHED(c, "sweep_z");
     }
+    if (e1) CU_TRY(cudaEventRecord(e1, c->stream));
     // S' carries the periodic images of its own edge columns (single slab); in a ring they are pushed
     // by the next x sweep
     c->xhalo_valid[pO] = c->xhalo6_valid[pO] = (c->p.periodic_x != 0);
