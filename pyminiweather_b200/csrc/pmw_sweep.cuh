@@ -92,23 +92,21 @@ __device__ __forceinline__ void push_halo6_role(const SweepArgs& a, int npush)
 //   interior column c0-6+t, FW = 64P+4 tile columns).  Persistent kernel: every WARP walks its own
 //   list of items (grid-stride) and never synchronises with another warp.  Per warp, in shared
 //   memory: two state rows S[2][4][FW] -- the row of the next item is in flight (one TMA box, own
-//   mbarrier) while the current one is computed -- and one row T[4][FW+2] for the intermediate
-//   states: stage 1 writes T1 there, stage 2 overwrites it IN PLACE with T2 shifted two columns
-//   to the right (the warp walks right to left, so a pass only overwrites columns no later pass
-//   reads), stage 3 reads T2 at the shifted position and stores the owned cells to HBM.
+//   mbarrier) while the current one is computed -- and the rows T1[4][FW], T2[4][FW] of the
+//   intermediate states; stage 3 stores the owned cells to HBM.  (The transposing z sweep further
+//   down keeps T1 and T2 in ONE row, in place; here the second row is affordable and removes the
+//   warp-level ordering that needs.)
 // ------------------------------------------------------------------------------------------
 template <int P>
 struct XSweepTile {
     static constexpr int FW = 64 * P + 4;   // tile columns (state box width)
     static constexpr int LC = 64 * P - 10;  // owned cells per row
-    static constexpr int TW = FW + 2;       // T row: two extra columns for the shifted T2
 #ifndef PMW_XSWEEP_WARPS
 #define PMW_XSWEEP_WARPS 4
 #endif
     static constexpr int WARPS = PMW_XSWEEP_WARPS;  // per CTA (no block-level synchronisation: any number works)
     static constexpr int S_ELEMS = NVAR * FW;
-    static constexpr int T_ELEMS = (NVAR * TW + 15) / 16 * 16;
-    static constexpr int WARP_ELEMS = 2 * S_ELEMS + T_ELEMS;
+    static constexpr int WARP_ELEMS = 4 * S_ELEMS;  // S[2] (double-buffered state row), T1, T2
     static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16); }
 };
 
@@ -168,13 +166,13 @@ __global__ void __launch_bounds__(32 * XSweepTile<P>::WARPS, PMW_XSWEEP_MINB)
 sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int ntx, const int npush)
 {
     using T = XSweepTile<P>;
-    constexpr int FW = T::FW, TW = T::TW;
+    constexpr int FW = T::FW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* const sS = reinterpret_cast<double*>(smem_raw) + warp * T::WARP_ELEMS;
-    double* const sT = sS + 2 * T::S_ELEMS;
+    double* const sT = sS + 2 * T::S_ELEMS;  // T1, then T2
     uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS) + 2 * warp;
-    static_assert((T::S_ELEMS * 8) % 128 == 0 && (T::WARP_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
+    static_assert((T::S_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
 
     const int nx = a.L.nx, nz = a.L.nz;
     const int nitems = nz * ntx;
@@ -186,10 +184,12 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         mbar_init(bars, 1);
         mbar_init(bars + 1, 1);
     }
-    // columns of T no stage writes (zero: they only feed interfaces whose results are discarded)
-    for (int e = lane; e < NVAR * 8; e += 32) {
-        const int v = e >> 3, j = e & 7;
-        sT[v * TW + (j < 2 ? j : 64 * P - 2 + j)] = 0.0;  // tile columns 0, 1 and 64P .. 64P+5
+    // columns of T1 / T2 no stage writes (zero: they only feed interfaces whose results are discarded):
+    // T1 0, 1 and 64P .. 64P+3; T2 0 .. 3 and 64P-2 .. 64P+3
+    for (int e = lane; e < NVAR * 16; e += 32) {
+        const int v = e >> 4, j = e & 15;
+        if (j < 6) sT[v * FW + (j < 2 ? j : 64 * P - 2 + j)] = 0.0;
+        else sT[T::S_ELEMS + v * FW + (j < 10 ? j - 6 : 64 * P - 12 + j)] = 0.0;
     }
     __syncwarp();
     pdl_wait();  // everything below reads state produced by the previous kernel
@@ -228,7 +228,6 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         phase ^= 1u << buf;
 
         const double* src = rowS;  // forcing row of the stage (+ 2*lane)
-        int vs = FW;               // its plane stride
         double dts = a.dt1;
         int tlo = 2, thi = 64 * P;
 #pragma unroll 1
@@ -241,7 +240,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    const double* p = src + v * vs + 64 * q;
+                    const double* p = src + v * FW + 64 * q;
                     const Pair u01 = lds2(p), u23 = lds2(p + 2);
                     t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
                 }
@@ -250,9 +249,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 const int i = i0 + 64 * q;
                 bool ok = t >= tlo && t < thi;
                 if (s == 2) ok = ok && i < nx;
-                // stage 1 -> T1 at column t, stage 2 -> T2 at column t+2 (in place), stage 3 -> HBM
-                double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + 64 * q + 2 + 2 * s;
-                const long long dvs = (s == 2) ? a.L.vstride : (long long)TW;
+                // stage 1 -> T1, stage 2 -> T2 (column t), stage 3 -> HBM
+                double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + s * T::S_ELEMS + 64 * q + 2;
+                const long long dvs = (s == 2) ? a.L.vstride : (long long)FW;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const double give = (lane == 0) ? keep[v] : f0[v];
@@ -276,8 +275,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 }
             }
             __syncwarp();
-            src = rowT + 2 * s;  // T1 at its own columns, T2 shifted by two
-            vs = TW;
+            src = rowT + s * T::S_ELEMS;
             dts = (s == 0) ? a.dt2 : a.dt3;
             tlo += 2;
             thi -= 2;
@@ -429,6 +427,7 @@ sweep_zt(const __grid_constant__ CUtensorMap tm_box, const SweepArgs a, const in
                     const Pair u01 = lds2(p), u23 = lds2(p + 2);
                     t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
                 }
+                if (s == 1) __syncwarp();  // stage 2 overwrites T in place: every lane holds its taps first
                 // interface index of tile column j is r0 - 4 + j; the pair's left cell has the same index
                 const int j0 = 64 * q + 2 * lane;
                 const int k0 = r0 - 4 + j0;

@@ -25,4 +25,17 @@ for variant in ("tma", "direct"):
         print(variant, nx, nz, "err %.2e" % err, st, flush=True)
         assert err < 1e-11
         s.close(); b.close()
+        if variant == "tma":  # the other sweep organisations: transposing z sweep, stage-by-stage kernels
+            _, c2 = new_case(nx, nz, "collision")
+            no.evolve(c2); no.evolve(c2); no.evolve(c2)
+            for tune in (dict(fuse=1, sweep_zt=1), dict(fuse=1, sweep_zt=0, sweep_lz=9), dict(fuse=0)):
+                t = DeviceSolver(nx, nz, case.dx, case.dz, case.dt, variant=variant)
+                t.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); t.set_tuning(**tune)
+                _, c0 = new_case(nx, nz, "collision")
+                t.upload(0, c0.state); t.upload(1, c0.state_tmp)
+                t.evolve(3)
+                e2 = worst_rel_l2(t.download(0), c2.state)
+                print("  ", tune, "err %.2e" % e2, flush=True)
+                assert e2 < 1e-11
+                t.close()
 print("sanitize case ok")
