@@ -120,7 +120,11 @@ int pmw_discrete_step(pmw_ctx *ctx, int direction, int init_buf, int forcing_buf
 /* nsteps x evolve (pyminiweather/solve/step.py:85-143): two directional sweeps of three RK
  * stages per step, Z first on the first call, order alternating per step; the direction
  * flag (a module global in the reference, step.py:18) lives in the context.  Halo fill is
- * folded into the stage kernels.  dt <= 0 means params.dt. */
+ * folded into the kernels.  dt <= 0 means params.dt.
+ * Default on the TMA variant: ONE kernel per directional sweep (the three RK stages fused, the
+ * two intermediate states on chip, 6-cell halo recomputed; bit-identical to running the stages
+ * one by one) -- tuning key "fuse".  The reference's state_tmp (its stage-2 array) is then
+ * written by the last sweep of the call only ("keep_tmp"). */
 int pmw_evolve(pmw_ctx *ctx, int nsteps, double dt);
 /* One RK stage (rk_stage = 1,2,3) of the fused step on the context's rotating buffers, for
  * callers that interleave their own work between stages (slab halo exchange).  The caller
@@ -179,7 +183,11 @@ int pmw_peer_status(pmw_ctx *ctx, int *timed_out);
  * (0|1: programmatic dependent launch between consecutive stage kernels; default 1), "l2_hints"
  * (decimal abcd = L2 eviction priority of: forcing in stage 1, forcing in stages 2-3, init, out;
  * 0 normal, 1 evict_first, 2 evict_last; default 1100), "chunks" (1..4 independent bands per directional sweep, each a kernel chain on
- * its own stream so that kernel tails overlap; default 2 for grids of >= 2^20 cells), "peer_dbg" (development switches). */
+ * its own stream so that kernel tails overlap; default 2 for grids of >= 2^20 cells), "peer_dbg" (development switches).
+ * Fused sweeps: "fuse" (0|1, default 1: pmw_evolve launches one kernel per directional sweep), "keep_tmp"
+ * (0|1, default 1: the last sweep of a pmw_evolve call also writes state_tmp), "sweep_zt" (z sweep
+ * organisation: 0 streaming [default], 1 transposing), "sweep_lz" (rows per segment of the streaming z sweep;
+ * 0 = chosen from the grid), "sweep_xp" (passes of 64 interfaces per x tile: 2). */
 int pmw_set_tuning(pmw_ctx *ctx, const char *key, int value);
 int pmw_get_tuning(pmw_ctx *ctx, const char *key, int *value);
 
