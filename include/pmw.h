@@ -96,6 +96,14 @@ int pmw_set_hydrostatic(pmw_ctx *ctx, const double *hy_dens_cell, const double *
  * (pyminiweather/solve/source.py:43-75, called at solve/step.py:78) adds to the rho*w tendency in
  * every stage; host [nz][nx], NULL clears it. */
 int pmw_set_source_w(pmw_ctx *ctx, const double *host_nz_nx);
+/* ic_type "injection" only: switches pmw_bc_x (and the halo fill inside pmw_evolve /
+ * pmw_discrete_step) to the inflow branch of set_bc_x (pyminiweather/ics/bcs.py:37,41-64): the left
+ * halo is the periodic image, the right halo is left untouched, and on the jet rows the left halo of
+ * rho*u / (rho*theta)' is forced to (rho'+rho_hy)*u_in and (rho'+rho_hy)*theta_in - (rho*theta)_hy.
+ * host_rows[nz]: 1 on the interior rows of the jet -- the caller evaluates the reference's row
+ * condition (bcs.py:43-48; the reference uses u_in = 50, theta_in = 298).  NULL restores periodic x.
+ * Single-context only (periodic_x = 1, no slab ring). */
+int pmw_set_inflow(pmw_ctx *ctx, const unsigned char *host_rows, double u_in, double theta_in);
 /* host [4][nz+4][nx+4] <-> device buffer `buf` (PMW_BUF_*).  Synchronous. */
 int pmw_upload_state(pmw_ctx *ctx, int buf, const double *host);
 int pmw_download_state(pmw_ctx *ctx, int buf, double *host);
@@ -104,7 +112,8 @@ int pmw_upload_state_async(pmw_ctx *ctx, int buf, const double *host);
 int pmw_download_state_async(pmw_ctx *ctx, int buf, double *host);
 
 /* -- operators (one call = one reference function) ------------------------------- */
-/* set_bc_x, periodic branch (pyminiweather/ics/bcs.py:35-39). */
+/* set_bc_x (pyminiweather/ics/bcs.py:8-64): periodic branch (:35-39), or the injection branch
+ * (:37,41-64) on a context with pmw_set_inflow rows. */
 int pmw_bc_x(pmw_ctx *ctx, int buf);
 /* set_bc_z (pyminiweather/ics/bcs.py:92-148). */
 int pmw_bc_z(pmw_ctx *ctx, int buf);

@@ -10,7 +10,7 @@
  * NumPy's SIMD pow may differ by an ulp.
  *
  * Reference locations (relative to the reference repo root):
- *   set_bc_x            pyminiweather/ics/bcs.py:35-39
+ *   set_bc_x            pyminiweather/ics/bcs.py:35-39 (periodic), :37,41-64 (injection inflow)
  *   set_bc_z            pyminiweather/ics/bcs.py:92-148
  *   interpolate_x/z     pyminiweather/solve/interpolate.py:33-43, 69-79
  *                       (stencil weights: pyminiweather/data/fields.py:94-97)
@@ -67,11 +67,15 @@ typedef struct {
     double *tend;                     /* scratch [4][nz][nx]     */
     const double *source_w;           /* [nz][nx] or NULL: gravity-wave forcing on rho*w in every
                                          stage (source.py:43-50, step.py:78) */
+    const unsigned char *inflow_rows; /* [nz+4] or NULL: 1 on the array rows of the injection jet
+                                         (bcs.py:43-48, evaluated by the caller); non-NULL selects
+                                         the injection branch of set_bc_x */
 } pmwo_case;
 
 #define S(s, v, k, i) (s)[((size_t)(v) * NZ + (size_t)(k)) * NX + (size_t)(i)]
 
-/* bcs.py:35-39 */
+/* bcs.py:35-39; injection: the right halo is left alone (:37) and the jet rows of the left halo are
+ * forced to u = 50 m/s, theta = 298 K (:50-64) */
 void pmwo_set_bc_x(const pmwo_case *c, double *s)
 {
     const int nx = c->nx, nz = c->nz;
@@ -80,8 +84,19 @@ void pmwo_set_bc_x(const pmwo_case *c, double *s)
         for (int k = HS; k < nz + HS; ++k) {
             S(s, v, k, 0) = S(s, v, k, nx);
             S(s, v, k, 1) = S(s, v, k, nx + 1);
-            S(s, v, k, nx + HS) = S(s, v, k, HS);
-            S(s, v, k, nx + HS + 1) = S(s, v, k, HS + 1);
+            if (!c->inflow_rows) {
+                S(s, v, k, nx + HS) = S(s, v, k, HS);
+                S(s, v, k, nx + HS + 1) = S(s, v, k, HS + 1);
+            }
+        }
+    if (c->inflow_rows)
+        for (int k = HS; k < nz + HS; ++k) {
+            if (!c->inflow_rows[k]) continue;
+            for (int i = 0; i < 2; ++i) {
+                const double rho = S(s, DENS, k, i) + c->hy_dens_cell[k];
+                S(s, UMOM, k, i) = rho * 50.0;
+                S(s, RHOT, k, i) = rho * 298.0 - c->hy_dens_theta_cell[k];
+            }
         }
 }
 

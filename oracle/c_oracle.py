@@ -23,7 +23,8 @@ class _Case(C.Structure):
                 ("dx", C.c_double), ("dz", C.c_double), ("dt", C.c_double),
                 ("hy_dens_cell", _dp), ("hy_dens_theta_cell", _dp),
                 ("hy_dens_int", _dp), ("hy_dens_theta_int", _dp), ("hy_pressure_int", _dp),
-                ("flux", _dp), ("tend", _dp), ("source_w", _dp)]
+                ("flux", _dp), ("tend", _dp), ("source_w", _dp),
+                ("inflow_rows", C.POINTER(C.c_ubyte))]
 
 
 def build(force: bool = False) -> str:
@@ -59,11 +60,17 @@ class COracle:
         self.case = case
         self._flux = np.zeros(4 * (case.nz + 1) * (case.nx + 1))
         self._tend = np.zeros(4 * case.nz * case.nx)
+        self._inflow = None
+        if getattr(case, "inflow_zlen", None) is not None:  # injection: row mask of the jet (bcs.py:43-48)
+            from .numpy_oracle import inflow_rows
+            self._inflow = np.zeros(case.nz + 4, dtype=np.uint8)
+            self._inflow[inflow_rows(case.nz, case.dz, case.inflow_zlen)] = 1
         self._c = _Case(case.nx, case.nz, case.dx, case.dz, case.dt,
                         _p(case.hy_dens_cell), _p(case.hy_dens_theta_cell),
                         _p(case.hy_dens_int), _p(case.hy_dens_theta_int),
                         _p(case.hy_pressure_int), _p(self._flux), _p(self._tend),
-                        _p(case.source_w) if getattr(case, "source_w", None) is not None else None)
+                        _p(case.source_w) if getattr(case, "source_w", None) is not None else None,
+                        self._inflow.ctypes.data_as(C.POINTER(C.c_ubyte)) if self._inflow is not None else None)
 
     def evolve(self, nsteps: int = 1, dt: float | None = None):
         rev = C.c_int(1 if self.case.reverse_direction else 0)

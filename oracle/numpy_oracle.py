@@ -72,6 +72,9 @@ class OracleCase:
     # ic_type == "gravity" only: wpert(x,z) * hy_dens_cell[2:nz+2, None], added to the w-momentum
     # tendency in EVERY stage, both directions (source.py:43-50, called at step.py:78)
     source_w: np.ndarray | None = None
+    # ic_type == "injection" only: the domain height; switches set_bc_x to the inflow branch
+    # (bcs.py:37,41-64).  None = periodic x.
+    inflow_zlen: float | None = None
     scratch: dict = field(default_factory=dict)
 
     def copy(self) -> "OracleCase":
@@ -82,18 +85,36 @@ class OracleCase:
             self.hy_dens_int.copy(), self.hy_dens_theta_int.copy(),
             self.hy_pressure_int.copy(), self.reverse_direction,
             None if self.source_w is None else self.source_w.copy(),
+            self.inflow_zlen,
         )
 
 
 # ---- boundary conditions ------------------------------------------------------
+def inflow_rows(nz: int, dz: float, zlen: float) -> np.ndarray:
+    """Array rows (halo offset included) of the injection jet, bcs.py:43-48.  The reference samples
+    ``z = linspace(0, nz*dz, nz, endpoint=False) + 0.5`` (cell BOTTOMS plus half a metre, not cell
+    centres) and keeps rows with |z - 3/4 zlen| <= zlen/16."""
+    z = np.linspace(start=0, stop=nz * dz, num=nz, endpoint=False) + 0.5
+    return np.nonzero(np.fabs(z - 3.0 * zlen / 4.0) <= zlen / 16.0)[0] + HS
+
+
 def set_bc_x(case: OracleCase, s: np.ndarray) -> None:
-    """Periodic wrap of the two halo columns, interior rows only (bcs.py:35-39)."""
+    """Periodic wrap of the two halo columns, interior rows only (bcs.py:35-39); for the injection
+    configuration the right halo is left alone and the left halo of the jet rows is forced to
+    u = 50 m/s, theta = 298 K (bcs.py:37,41-64)."""
     nx, nz = case.nx, case.nz
     rows = slice(HS, nz + HS)
     s[:, rows, 0] = s[:, rows, nx]
     s[:, rows, 1] = s[:, rows, nx + 1]
-    s[:, rows, nx + HS] = s[:, rows, HS]
-    s[:, rows, nx + HS + 1] = s[:, rows, HS + 1]
+    if case.inflow_zlen is None:
+        s[:, rows, nx + HS] = s[:, rows, HS]
+        s[:, rows, nx + HS + 1] = s[:, rows, HS + 1]
+        return
+    idx = inflow_rows(nz, case.dz, case.inflow_zlen)
+    for col in (0, 1):
+        s[UMOM, idx, col] = (s[DENS, idx, col] + case.hy_dens_cell[idx]) * 50.0
+    for col in (0, 1):
+        s[RHOT, idx, col] = (s[DENS, idx, col] + case.hy_dens_cell[idx]) * 298.0 - case.hy_dens_theta_cell[idx]
 
 
 def set_bc_z(case: OracleCase, s: np.ndarray) -> None:

@@ -106,4 +106,5 @@ class ReferenceRun:
             hy_dens_theta_int=np.array(f.hy_dens_theta_int, copy=True),
             hy_pressure_int=np.array(f.hy_pressure_int, copy=True),
             reverse_direction=self._reverse, source_w=src,
+            inflow_zlen=float(p["zlen"]) if p["ic_type"] == "injection" else None,
         )

@@ -22,16 +22,38 @@ from .engine import HYDRO_NAMES, DeviceSolver
 _foreign: dict[int, tuple] = {}
 _MAX_FOREIGN = 4  # contexts kept alive for foreign fields objects
 
-UNSUPPORTED_ICS = ("injection",)
+SUPPORTED_ICS = ("thermal", "collision", "density-current", "gravity", "injection")
+
+# the inflow jet of the injection configuration (bcs.py:50-64)
+INFLOW_U, INFLOW_THETA = 50.0, 298.0
 
 
 def check_ic(ic_type):
-    """The injection inflow BC (bcs.py:37,41-64: non-periodic x halos with forced inflow rows) is not
-    part of the accelerated path (the reference's README lists it as unsupported, README.md:291)."""
-    if ic_type in UNSUPPORTED_ICS:
-        raise NotImplementedError(
-            f"ic_type={ic_type!r} is not supported by the B200 hot path (periodic-x / solid-wall-z "
-            "configurations only: thermal, collision, density-current, gravity)")
+    """The five --ic-type choices of the reference (__main__.py:87, initial.py:41-47)."""
+    if ic_type not in SUPPORTED_ICS:
+        raise ValueError(f"unknown ic_type {ic_type!r}; expected one of {SUPPORTED_ICS}")
+
+
+def inflow_row_mask(params) -> np.ndarray:
+    """uint8[nz], 1 on the interior rows of the injection jet -- the reference's own row condition
+    (bcs.py:43-48), quirks included: it samples ``linspace(0, nz*dz, nz, endpoint=False) + 0.5``
+    (cell bottoms plus half a metre) and keeps |z - 3/4 zlen| <= zlen/16."""
+    nz, dz, zlen = int(params["nz"]), params["dz"], params["zlen"]
+    z = np.linspace(start=0, stop=nz * dz, num=nz, endpoint=False) + 0.5
+    return (np.fabs(z - 3.0 * zlen / 4.0) <= zlen / 16.0).astype(np.uint8)
+
+
+def sync_inflow(solver, params, ic_type):
+    """Switch the context's x halo fill between the periodic and the injection branch of set_bc_x
+    (bcs.py:37,41-64) according to ``ic_type``."""
+    if ic_type == "injection":
+        key = (int(params["nz"]), float(params["dz"]), float(params["zlen"]))
+        if getattr(solver, "_inflow_key", None) != key:
+            solver.set_inflow(inflow_row_mask(params), INFLOW_U, INFLOW_THETA)
+            solver._inflow_key = key
+    elif getattr(solver, "_inflow_key", None) is not None:
+        solver.set_inflow(None)
+        solver._inflow_key = None
 
 
 def sync_source(solver, params, hy_dens_cell):
@@ -82,6 +104,7 @@ def foreign_solver(fields, params) -> DeviceSolver:
     if all(np.all(h > 0) for h in hydro[:4]) and not solver.hydro_matches(hydro):
         solver.set_hydrostatic(*hydro)
     sync_source(solver, params, hydro[0])
+    sync_inflow(solver, params, params.get("ic_type"))
     return solver
 
 

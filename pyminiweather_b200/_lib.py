@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libpmw.so")
 SOURCES = ["pmw_api.cu"]
-HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_aux.cuh", "pmw_unfused.cuh"]
+HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_sweep.cuh", "pmw_aux.cuh", "pmw_unfused.cuh"]
 
 PMW_BUF_STATE, PMW_BUF_TMP = 0, 1
 PMW_DIR_X, PMW_DIR_Z = 1, 2
@@ -47,6 +47,7 @@ SIGNATURES = {
     "pmw_synchronize": (C.c_int, [_vp]),
     "pmw_set_hydrostatic": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "pmw_set_source_w": (C.c_int, [_vp, _vp]),
+    "pmw_set_inflow": (C.c_int, [_vp, _vp, C.c_double, C.c_double]),
     "pmw_upload_state": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_download_state": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_upload_state_async": (C.c_int, [_vp, C.c_int, _vp]),

@@ -78,6 +78,8 @@ struct pmw_ctx {
     int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt;
     double* hydro_blob;
     double* src_w;  // gravity-wave forcing field or nullptr
+    unsigned char* jet_rows;  // injection: [nz] mask of the inflow rows, or nullptr (periodic x)
+    double jet_u, jet_theta;
     Hydro hy;
     bool hydro_set;
     cudaStream_t stream;
@@ -165,6 +167,8 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     for (int b = 0; b < 3; ++b) c->alloc[b] = nullptr;
     c->hydro_blob = nullptr;
     c->src_w = nullptr;
+    c->jet_rows = nullptr;
+    c->jet_u = c->jet_theta = 0.0;
     c->stats_partial = c->stats_out = nullptr;
     c->flags = nullptr;
     c->edge_counters = nullptr;
@@ -246,6 +250,7 @@ extern "C" int pmw_destroy(pmw_ctx* c)
         if (c->alloc[b]) cudaFree(c->alloc[b]);
     if (c->hydro_blob) cudaFree(c->hydro_blob);
     if (c->src_w) cudaFree(c->src_w);
+    if (c->jet_rows) cudaFree(c->jet_rows);
     if (c->stats_partial) cudaFree(c->stats_partial);
     if (c->stats_out) cudaFree(c->stats_out);
     for (int k = 0; k < 4; ++k) {
@@ -398,6 +403,25 @@ extern "C" int pmw_set_source_w(pmw_ctx* c, const double* host)
     return PMW_OK;
 }
 
+extern "C" int pmw_set_inflow(pmw_ctx* c, const unsigned char* host_rows, double u_in, double theta_in)
+{
+    BIND(c);
+    if (!host_rows) {
+        if (c->jet_rows) cudaFree(c->jet_rows);
+        c->jet_rows = nullptr;
+        return PMW_OK;
+    }
+    NEED(c->p.periodic_x && !c->peers, "pmw_set_inflow: the injection inflow needs the whole domain in one context "
+                                       "(periodic_x=1, no slab ring)");
+    if (!c->jet_rows) CU_TRY(cudaMalloc(&c->jet_rows, (size_t)c->p.nz));
+    CU_TRY(cudaMemcpyAsync(c->jet_rows, host_rows, (size_t)c->p.nz, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->jet_u = u_in;
+    c->jet_theta = theta_in;
+    for (int b = 0; b < 3; ++b) c->xhalo_valid[b] = c->xhalo6_valid[b] = false;
+    return PMW_OK;
+}
+
 static int check_buf(int buf)
 {
     if (buf != PMW_BUF_STATE && buf != PMW_BUF_TMP) return fail(PMW_EINVAL, "unknown buffer id %d", buf);
@@ -475,6 +499,14 @@ extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
 {
     BIND(c);
     CHECK_BUF(buf);
+    if (c->jet_rows) {  // injection branch of set_bc_x (bcs.py:37,41-64)
+        NEED(c->hydro_set, "pmw_bc_x: the inflow rows need the hydrostatic profiles (pmw_set_hydrostatic)");
+        bc_x_inflow_kernel<<<(c->p.nz + 127) / 128, 128, 0, c->stream>>>(
+            c->base[c->l2p[buf]], c->L, c->hy.dens_cell, c->hy.dens_theta_cell, c->jet_rows, c->jet_u, c->jet_theta);
+        LAUNCHED(c, "bc_x_inflow_kernel");
+        c->xhalo_valid[c->l2p[buf]] = c->xhalo6_valid[c->l2p[buf]] = false;  // not a periodic image
+        return PMW_OK;
+    }
     const int n = NVAR * c->p.nz;
     bc_x_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[c->l2p[buf]], c->L);
     LAUNCHED(c, "bc_x_kernel");
@@ -1126,6 +1158,26 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
     NEED(c->p.periodic_x || c->peers,
          "pmw_evolve: a slab context (periodic_x=0) needs pmw_connect_peers, or must be stepped stage by "
          "stage with pmw_evolve_stage and a halo exchange before every x stage");
+    if (c->jet_rows) {
+        // Injection: x is not periodic, so neither the fused sweeps (6-wide periodic halo) nor the
+        // stages that write the wrap for their successor apply.  Run the reference's own sequence
+        // (step.py:105-143): explicit halo fill, then the fused stage kernel, per stage; arrays that
+        // are updated in place keep their halo ring, so the right halo columns keep their initial
+        // values exactly as in the reference.
+        NEED(c->p.periodic_x && !c->peers, "pmw_evolve: the injection inflow is single-context only");
+        if (dt <= 0) dt = c->p.dt;
+        for (int n = 0; n < nsteps; ++n) {
+            const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
+            for (int d = 0; d < 2; ++d) {
+                int rc = pmw_discrete_step(c, dirs[d], PMW_BUF_STATE, PMW_BUF_STATE, PMW_BUF_TMP, dt / 3);
+                if (rc == PMW_OK) rc = pmw_discrete_step(c, dirs[d], PMW_BUF_STATE, PMW_BUF_TMP, PMW_BUF_TMP, dt / 2);
+                if (rc == PMW_OK) rc = pmw_discrete_step(c, dirs[d], PMW_BUF_STATE, PMW_BUF_TMP, PMW_BUF_STATE, dt / 1);
+                if (rc != PMW_OK) return rc;
+            }
+            c->reverse = !c->reverse;
+        }
+        return PMW_OK;
+    }
     // (x sweeps of a connected slab carry the halo push / epoch wait per stage: those stay whole)
     const bool chunk_ok = c->chunks > 1 && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && !c->timing;
     const bool fused = fuse_ok(c);
@@ -1310,6 +1362,7 @@ extern "C" int pmw_connect_peers(pmw_ctx* c, void* const left[4], void* const ri
 {
     BIND(c);
     NEED(!c->p.periodic_x, "pmw_connect_peers: the context was created with periodic_x=1");
+    NEED(!c->jet_rows, "pmw_connect_peers: the injection inflow is single-context only");
     NEED((c->p.nx & 1) == 0, "pmw_connect_peers: the slab width must be even");
     NEED(left && right, "pmw_connect_peers: null argument");
     for (int b = 0; b < 3; ++b) {

@@ -18,6 +18,36 @@ __global__ void bc_x_kernel(double* s, const Layout L)
     row[nx + HS + 1] = row[HS + 1];
 }
 
+// set_bc_x, injection branch (bcs.py:35-37,41-64): the left halo is the periodic image of the last two
+// interior columns; the right halo is NOT touched (it keeps whatever the array held); on the rows of
+// the jet (mask, evaluated on the host exactly as bcs.py:43-48 does) the left halo of rho*u and
+// (rho*theta)' is then forced to u_in, theta_in using the halo's own rho'.  One thread per row.
+__global__ void bc_x_inflow_kernel(double* s, const Layout L, const double* __restrict__ hd,
+                                   const double* __restrict__ hdt, const unsigned char* __restrict__ jet,
+                                   double u_in, double theta_in)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.nz) return;
+    const int k = t + HS, nx = L.nx;
+    double dens[2];
+#pragma unroll
+    for (int v = 0; v < NVAR; ++v) {
+        double* row = s + idx(L, v, k, 0);
+        const double a = row[nx], b = row[nx + 1];
+        row[0] = a;
+        row[1] = b;
+        if (v == DENS) { dens[0] = a; dens[1] = b; }
+    }
+    if (jet[t]) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double rho = dens[j] + hd[k];
+            s[idx(L, UMOM, k, j)] = rho * u_in;
+            s[idx(L, RHOT, k, j)] = rho * theta_in - hdt[k];
+        }
+    }
+}
+
 // The same periodic wrap, six columns wide: what a fused x sweep (pmw_sweep.cuh) reads.  Array
 // columns -4 .. 1 are the image of nx-4 .. nx+1, columns nx+2 .. nx+7 the image of 2 .. 7.
 __global__ void bc_x6_kernel(double* s, const Layout L)

@@ -107,8 +107,9 @@ class Fields:
             self._solver.set_hydrostatic(*hydro)
         ic = params.get("ic_type")
         if ic != self.__dict__.get("_source_ic"):  # the forcing field only depends on the configuration
-            from .._dispatch import sync_source
+            from .._dispatch import sync_inflow, sync_source
             sync_source(self._solver, params, self.hy_dens_cell)
+            sync_inflow(self._solver, params, ic)
             self._source_ic = ic if np.all(self.hy_dens_cell > 0) else None
         for buf in (PMW_BUF_STATE, PMW_BUF_TMP):
             if self._host_dirty[buf]:

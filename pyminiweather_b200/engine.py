@@ -58,6 +58,7 @@ class DeviceSolver:
         self._lib = lib
         self._hydro = None
         self._source = None
+        self._inflow_key = None
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -97,6 +98,17 @@ class DeviceSolver:
         field = _as_f64(field, (self.nz, self.nx), "source_w")
         check(self._lib.pmw_set_source_w(self._h, C.c_void_p(field.ctypes.data)))
         self._source = field.copy()
+
+    def set_inflow(self, row_mask, u_in: float = 50.0, theta_in: float = 298.0):
+        """Injection configuration: uint8[nz] mask of the jet rows (``set_bc_x`` then takes the
+        inflow branch, bcs.py:37,41-64), or None for periodic x."""
+        if row_mask is None:
+            check(self._lib.pmw_set_inflow(self._h, None, 0.0, 0.0))
+            return
+        m = np.ascontiguousarray(row_mask, dtype=np.uint8)
+        if m.shape != (self.nz,):
+            raise ValueError(f"row_mask: expected shape ({self.nz},), got {m.shape}")
+        check(self._lib.pmw_set_inflow(self._h, C.c_void_p(m.ctypes.data), float(u_in), float(theta_in)))
 
     def hydro_matches(self, arrs) -> bool:
         return self._hydro is not None and all(np.array_equal(a, b) for a, b in zip(self._hydro, arrs))

@@ -73,6 +73,10 @@ def evolve(params, fields, mesh, dt: float = 1e-4) -> None:
     shape = (4, params["nz"] + 2 * params["hs"], params["nx"] + 2 * params["hs"])
     state = writable_f64(fields.state, shape, "fields.state")
     solver.upload(PMW_BUF_STATE, state)
+    if params["ic_type"] == "injection":
+        # the right halo columns of state_tmp are never refreshed in this configuration (bcs.py:37):
+        # they are caller data that the x stages read
+        solver.upload(PMW_BUF_TMP, writable_f64(fields.state_tmp, shape, "fields.state_tmp"))
     solver.evolve(1, dt)
     solver.download(PMW_BUF_STATE, out=state)
     if SYNC_STATE_TMP:

@@ -35,7 +35,11 @@ def case_from_golden(g, state_key="state0", tmp_key=None, ic_type="thermal"):
     p = params_from_golden(g, ic_type)
     st = g[state_key]
     tmp = g[tmp_key] if tmp_key else st
-    return p, case_from_arrays(p, st, tmp, g)
+    case = case_from_arrays(p, st, tmp, g)
+    if ic_type == "injection":
+        p["zlen"] = float(g["zlen"])
+        case.inflow_zlen = p["zlen"]
+    return p, case
 
 
 def new_case(nx, nz, ic_type="thermal", **kw):
@@ -50,6 +54,8 @@ def new_case(nx, nz, ic_type="thermal", **kw):
     case = case_from_arrays(p, f._host[0], f._host[1], hydro)
     if ic_type == "gravity":
         case.source_w = no.gravity_source(nx, nz, case.dx, case.dz, p["xlen"], p["zlen"], case.hy_dens_cell)
+    if ic_type == "injection":
+        case.inflow_zlen = float(p["zlen"])
     return p, case
 
 

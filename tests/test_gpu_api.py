@@ -135,8 +135,8 @@ def test_unsupported_configurations_raise():
     from pyminiweather_b200.engine import DeviceSolver
     from pyminiweather_b200.solve import evolve
     p, f, mesh = native_fields(32, 16, "thermal")
-    with pytest.raises(NotImplementedError):
-        evolve(dict(p, ic_type="injection"), f, mesh, dt=p["dt"])
+    with pytest.raises(ValueError, match="unknown ic_type"):
+        evolve(dict(p, ic_type="squall-line"), f, mesh, dt=p["dt"])
     with pytest.raises(PmwError, match="hs must be 2"):
         DeviceSolver(32, 16, 1.0, 1.0, 0.1, hs=3)
     with pytest.raises(PmwError, match=">= 4"):
@@ -267,3 +267,34 @@ def test_cli_driver_end_to_end(tmp_path, caplog):
     sv = np.loadtxt(str(out).replace(".txt", "_svars.txt"), delimiter=",")
     assert sv.shape == (2 * 4 * 50, 100)
     assert rel_l2(sv[:200].reshape(4, 50, 100), no.compute_solution_variables(case)) <= 1e-11
+
+
+def test_injection_through_the_operator_api():
+    """ic_type 'injection' (bcs.py:37,41-64) through the reference-shaped functions: native fields,
+    a foreign (strict drop-in) container, and set_bc_x's own ic_type argument."""
+    from pyminiweather_b200.ics import set_bc_x
+    from pyminiweather_b200.post import compute_stats
+    from pyminiweather_b200.solve import evolve
+    p, f, mesh = native_fields(64, 32, "injection")
+    _, case = new_case(64, 32, "injection")
+    ff = foreign_fields(case)
+    for _ in range(30):
+        evolve(p, f, mesh, dt=p["dt"])
+        evolve(p, ff, mesh, dt=p["dt"])
+        no.evolve(case)
+    assert worst_rel_l2(f.state, case.state) <= 1e-11
+    assert worst_rel_l2(ff.state, case.state) <= 1e-11
+    assert np.linalg.norm(f.state[1, 2:-2, 2:-2]) > 1.0  # the jet is in
+    m, e = compute_stats(p, f)
+    mo, eo = no.compute_stats(case)
+    assert abs(m - mo) / mo <= 1e-12 and abs(e - eo) / eo <= 1e-12
+    # set_bc_x branches on its ic_type ARGUMENT, like the reference
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(f.state.shape); b = a.copy(); c = a.copy()
+    set_bc_x(p, f, a, "injection"); no.set_bc_x(case, b)
+    assert np.array_equal(a, b)
+    periodic = case.copy(); periodic.inflow_zlen = None
+    a = c.copy()
+    set_bc_x(p, f, a, "thermal"); no.set_bc_x(periodic, c)
+    assert np.array_equal(a, c)
+    f.close()

@@ -15,7 +15,7 @@ from oracle import numpy_oracle as no, reference_runner as rr
 pytestmark = pytest.mark.skipif(not rr.available(), reason="/root/reference not mounted")
 
 
-@pytest.mark.parametrize("ic", ["thermal", "collision", "density-current"])
+@pytest.mark.parametrize("ic", ["thermal", "collision", "density-current", "injection"])
 def test_numpy_oracle_bit_identical_to_reference(ic):
     ref = rr.ReferenceRun(96, 40, ic)
     case = ref.to_oracle_case()
