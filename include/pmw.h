@@ -104,6 +104,25 @@ int pmw_set_source_w(pmw_ctx *ctx, const double *host_nz_nx);
  * condition (bcs.py:43-48; the reference uses u_in = 50, theta_in = 298).  NULL restores periodic x.
  * Single-context only (periodic_x = 1, no slab ring). */
 int pmw_set_inflow(pmw_ctx *ctx, const unsigned char *host_rows, double u_in, double theta_in);
+/* Device-side `init` for the 2-D state (pyminiweather/ics/initial.py:57-80): fills BOTH logical buffers
+ * (state and state_tmp, halo cells included) by 3x3 Gauss-Legendre quadrature of the configuration
+ * described by `spec` -- squared-cosine potential-temperature bubbles (utils/utils.py:5-51) on a
+ * constant-theta or constant-Brunt-Vaisala background (ics/initial_conditions.py:26-81) with a uniform
+ * wind -- without the reference's 9x-the-state host temporaries.  x_axis[nx+4] / z_axis[nz+4] are the
+ * lower-left corner coordinates of the array's columns / rows as the reference's mesh yields them
+ * (mesh.py:22-40; a slab passes its own part of the x axis).  The 1-D hydrostatic profiles are still
+ * the caller's (pmw_set_hydrostatic). */
+#define PMW_IC_MAX_BUBBLES 4
+typedef struct pmw_ic_spec {
+    int nbubbles;                       /* 0..PMW_IC_MAX_BUBBLES */
+    double amp[PMW_IC_MAX_BUBBLES];     /* amplitude [K] */
+    double x0[PMW_IC_MAX_BUBBLES], z0[PMW_IC_MAX_BUBBLES];     /* centre */
+    double xrad[PMW_IC_MAX_BUBBLES], zrad[PMW_IC_MAX_BUBBLES]; /* radii */
+    double wind;                        /* uniform u [m/s] */
+    int bvfreq;                         /* 0: theta = theta0; 1: constant Brunt-Vaisala frequency bv0 */
+    double bv0;
+} pmw_ic_spec;
+int pmw_init_state(pmw_ctx *ctx, const pmw_ic_spec *spec, const double *x_axis, const double *z_axis);
 /* host [4][nz+4][nx+4] <-> device buffer `buf` (PMW_BUF_*).  Synchronous. */
 int pmw_upload_state(pmw_ctx *ctx, int buf, const double *host);
 int pmw_download_state(pmw_ctx *ctx, int buf, double *host);

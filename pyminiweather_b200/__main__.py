@@ -16,7 +16,7 @@ from pathlib import Path
 import numpy as np
 
 from .data import initialize_fields
-from .ics import init
+from .ics import init, init_device
 from .ics.initial_conditions import IC_TYPES
 from .mesh import MeshData
 from .post import compute_solution_variables, compute_stats
@@ -47,6 +47,9 @@ def get_parser() -> argparse.ArgumentParser:
     ap.add_argument("--ic-type", type=str, default="thermal", choices=list(IC_TYPES), dest="ic_type")
     ap.add_argument("--hs", type=int, default=2, choices=[2], dest="hs")
     ap.add_argument("--s", type=int, default=4, choices=[4], dest="s")
+    ap.add_argument("--device-init", action="store_true", default=False, dest="device_init",
+                    help="integrate the initial condition on the GPU (init_state_kernel) instead of the "
+                         "reference's host NumPy quadrature (not a reference flag)")
     ap.add_argument("--verbose", action="store_true", default=False, dest="verbose")
     ap.add_argument("--app-log-file", type=Path, default=None, metavar="FILE", dest="app_log_file")
     return ap
@@ -94,7 +97,7 @@ def main(argv=None) -> int:
     with TimedCodeBlock(label="Elapsed time for initialization"):
         fields = initialize_fields(params)
         mesh = MeshData(params)
-        init(fields, params, mesh)
+        (init_device if params.get("device_init") else init)(fields, params, mesh)
 
     mass0, energy0 = compute_stats(params, fields)
     log.info(f"Start: total_mass, total_energy: {mass0}, {energy0}")

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libpmw.so")
 SOURCES = ["pmw_api.cu"]
-HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_sweep.cuh", "pmw_aux.cuh", "pmw_unfused.cuh"]
+HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_sweep.cuh", "pmw_aux.cuh", "pmw_unfused.cuh", "pmw_init.cuh"]
 
 PMW_BUF_STATE, PMW_BUF_TMP = 0, 1
 PMW_DIR_X, PMW_DIR_Z = 1, 2
@@ -28,6 +28,18 @@ class PmwParams(C.Structure):
                 ("dx", C.c_double), ("dz", C.c_double), ("dt", C.c_double),
                 ("device", C.c_int), ("variant", C.c_int), ("pow_mode", C.c_int),
                 ("periodic_x", C.c_int)]
+
+
+PMW_IC_MAX_BUBBLES = 4
+
+
+class PmwIcSpec(C.Structure):
+    """pmw_ic_spec (include/pmw.h): the configuration pmw_init_state integrates."""
+    _fields_ = [("nbubbles", C.c_int),
+                ("amp", C.c_double * PMW_IC_MAX_BUBBLES),
+                ("x0", C.c_double * PMW_IC_MAX_BUBBLES), ("z0", C.c_double * PMW_IC_MAX_BUBBLES),
+                ("xrad", C.c_double * PMW_IC_MAX_BUBBLES), ("zrad", C.c_double * PMW_IC_MAX_BUBBLES),
+                ("wind", C.c_double), ("bvfreq", C.c_int), ("bv0", C.c_double)]
 
 
 class PmwError(RuntimeError):
@@ -48,6 +60,7 @@ SIGNATURES = {
     "pmw_set_hydrostatic": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "pmw_set_source_w": (C.c_int, [_vp, _vp]),
     "pmw_set_inflow": (C.c_int, [_vp, _vp, C.c_double, C.c_double]),
+    "pmw_init_state": (C.c_int, [_vp, C.POINTER(PmwIcSpec), _dp, _dp]),
     "pmw_upload_state": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_download_state": (C.c_int, [_vp, C.c_int, _vp]),
     "pmw_upload_state_async": (C.c_int, [_vp, C.c_int, _vp]),

@@ -18,6 +18,7 @@
 #include "pmw_tma.cuh"
 #include "pmw_sweep.cuh"
 #include "pmw_unfused.cuh"
+#include "pmw_init.cuh"
 
 using namespace pmw;
 
@@ -494,6 +495,48 @@ static int after_launch(pmw_ctx* c, const char* what)
         int rc_ = after_launch(c, what);   \
         if (rc_ != PMW_OK) return rc_;     \
     } while (0)
+
+struct DevBuf {
+    double* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(double)); }
+};
+
+extern "C" int pmw_init_state(pmw_ctx* c, const pmw_ic_spec* spec, const double* x_axis, const double* z_axis)
+{
+    BIND(c);
+    NEED(spec && x_axis && z_axis, "pmw_init_state: null argument");
+    NEED(spec->nbubbles >= 0 && spec->nbubbles <= PMW_IC_MAX_BUBBLES, "pmw_init_state: nbubbles must be in 0..%d",
+         PMW_IC_MAX_BUBBLES);
+    static_assert(PMW_IC_MAX_BUBBLES == IC_MAX_BUBBLES, "bubble capacity");
+    IcSpec s;
+    s.nbubbles = spec->nbubbles;
+    for (int n = 0; n < IC_MAX_BUBBLES; ++n) {
+        s.amp[n] = spec->amp[n]; s.x0[n] = spec->x0[n]; s.z0[n] = spec->z0[n];
+        s.xrad[n] = spec->xrad[n]; s.zrad[n] = spec->zrad[n];
+        if (n < spec->nbubbles) NEED(s.xrad[n] > 0 && s.zrad[n] > 0, "pmw_init_state: bubble %d has a non-positive radius", n);
+    }
+    s.wind = spec->wind;
+    s.bvfreq = spec->bvfreq ? 1 : 0;
+    s.bv0 = spec->bv0;
+    NEED(!s.bvfreq || s.bv0 > 0, "pmw_init_state: bv0 must be positive");
+    s.dx = c->p.dx;
+    s.dz = c->p.dz;
+    const int NX = c->p.nx + 2 * HS, NZ = c->p.nz + 2 * HS;
+    DevBuf axes;
+    CU_TRY(axes.alloc((size_t)NX + NZ));
+    CU_TRY(cudaMemcpyAsync(axes.p, x_axis, (size_t)NX * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(axes.p + NX, z_axis, (size_t)NZ * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const long long n = (long long)NX * NZ;
+    const int pS = c->l2p[PMW_BUF_STATE], pT = c->l2p[PMW_BUF_TMP];
+    init_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->base[pS], c->base[pT], c->L, s, axes.p,
+                                                                          axes.p + NX);
+    LAUNCHED(c, "init_state_kernel");
+    CU_TRY(cudaStreamSynchronize(c->stream));  // the axes buffer is freed on return
+    c->xhalo_valid[pS] = c->xhalo_valid[pT] = false;
+    c->xhalo6_valid[pS] = c->xhalo6_valid[pT] = false;
+    return PMW_OK;
+}
 
 extern "C" int pmw_bc_x(pmw_ctx* c, int buf)
 {
@@ -1407,12 +1450,6 @@ extern "C" int pmw_peer_status(pmw_ctx* c, int* timed_out)
 // ---------------------------------------------------------------------------------------------
 // unfused operator shims (API parity with the reference's individual operators; not the hot path)
 // ---------------------------------------------------------------------------------------------
-struct DevBuf {
-    double* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(double)); }
-};
-
 extern "C" int pmw_interpolate(pmw_ctx* c, int direction, int buf, double* host_vals, double* host_d3)
 {
     BIND(c);

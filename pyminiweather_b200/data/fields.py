@@ -117,6 +117,14 @@ class Fields:
                 self._host_dirty[buf] = False
         return self._solver
 
+    def init_on_device(self, params, bubbles, wind, bv0, x_axis, z_axis):
+        """Fill state and state_tmp in HBM with ``pmw_init_state`` (ics.init_device); the host arrays
+        become stale copies that are refreshed when read."""
+        self._host_dirty = {PMW_BUF_STATE: False, PMW_BUF_TMP: False}  # nothing worth uploading first
+        solver = self.device(params)
+        solver.init_state(bubbles, wind, bv0, x_axis, z_axis)
+        self.device_wrote(PMW_BUF_STATE, PMW_BUF_TMP)
+
     def device_wrote(self, *bufs):
         for buf in bufs:
             self._dev_newer[buf] = True

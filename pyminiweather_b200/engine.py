@@ -110,6 +110,24 @@ class DeviceSolver:
             raise ValueError(f"row_mask: expected shape ({self.nz},), got {m.shape}")
         check(self._lib.pmw_set_inflow(self._h, C.c_void_p(m.ctypes.data), float(u_in), float(theta_in)))
 
+    def init_state(self, bubbles, wind: float, bv0: float | None, x_axis, z_axis):
+        """Device-side ``init`` of the 2-D state (initial.py:57-80): ``bubbles`` is a list of
+        (amplitude, x0, z0, xrad, zrad); ``bv0`` selects the constant-Brunt-Vaisala background.
+        Fills both device buffers, halo cells included."""
+        spec = _lib.PmwIcSpec()
+        if len(bubbles) > _lib.PMW_IC_MAX_BUBBLES:
+            raise ValueError(f"at most {_lib.PMW_IC_MAX_BUBBLES} bubbles")
+        spec.nbubbles = len(bubbles)
+        for n, (amp, x0, z0, xrad, zrad) in enumerate(bubbles):
+            spec.amp[n], spec.x0[n], spec.z0[n], spec.xrad[n], spec.zrad[n] = amp, x0, z0, xrad, zrad
+        spec.wind = float(wind)
+        spec.bvfreq = 0 if bv0 is None else 1
+        spec.bv0 = 0.0 if bv0 is None else float(bv0)
+        xa = _as_f64(x_axis, (self.nx + 2 * self.hs,), "x_axis")
+        za = _as_f64(z_axis, (self.nz + 2 * self.hs,), "z_axis")
+        dp = C.POINTER(C.c_double)
+        check(self._lib.pmw_init_state(self._h, C.byref(spec), xa.ctypes.data_as(dp), za.ctypes.data_as(dp)))
+
     def hydro_matches(self, arrs) -> bool:
         return self._hydro is not None and all(np.array_equal(a, b) for a, b in zip(self._hydro, arrs))
 

@@ -71,3 +71,11 @@ def cell_quantities(ic_type, x, z, xlen):
     for amp, z0, xrad, zrad in bubbles:
         t = t + sample_ellipse_cosine(x, z, amp, xlen / 2, z0, xrad, zrad)
     return r, u, w, t, hr, ht
+
+
+def device_spec(ic_type, xlen):
+    """The same catalogue entry in the form ``pmw_init_state`` takes: ([(amp, x0, z0, xrad, zrad)],
+    uniform u, bv0 or None).  Every bubble is centred at xlen/2 (initial_conditions.py:131-132,197,266)."""
+    bubbles, wind, kind = _CATALOGUE[ic_type]
+    return ([(amp, xlen / 2, z0, xrad, zrad) for amp, z0, xrad, zrad in bubbles], wind,
+            _BV0 if kind == "bvfreq" else None)

@@ -34,6 +34,11 @@ class MeshData:
         return np.linspace((-self.hs + 0.5) * self.dz, (self.nz + self.hs + 0.5) * self.dz,
                            self.nz + 2 * self.hs, endpoint=False)
 
+    def get_axes_int_ext(self):
+        """The two 1-D axes get_mesh_int_ext() is the meshgrid of (x[nx+4], z[nz+4]); what the
+        device-side init takes instead of the 2-D arrays."""
+        return self._axis_int_ext(self.nx, self.dx), self._axis_int_ext(self.nz, self.dz)
+
     def get_mesh_int_ext(self):
         """(x, z) 2-D arrays over interior + ghost cells (lower-left corners)."""
         return self._int_ext
