@@ -1014,8 +1014,10 @@ static int evolve_sweep_chunked(pmw_ctx* c, int direction, double dt)
 // ---------------------------------------------------------------------------------------------
 static bool fuse_ok(const pmw_ctx* c)
 {
+    // (the gravity-wave forcing is folded into the sweeps of a single periodic slab; a slab of a ring
+    // would need its neighbours' forcing for the recomputed halo cells and runs stage by stage)
     return c->fuse && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && c->p.nx >= 16 && c->p.nz >= 8 &&
-           !c->src_w;
+           (!c->src_w || (c->p.periodic_x && !c->peers));
 }
 
 // Rows per z-sweep segment: a warp (32 columns x lz rows) is the unit of work and every SM holds
@@ -1069,6 +1071,8 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     a.nbr_flags_left = a.nbr_flags_right = nullptr;
     a.push_counter = c->edge_counters;
     a.dbg = c->peer_dbg;
+    a.src_w = c->src_w;
+    const bool has_src = c->src_w != nullptr;
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
     const CUtensorMap* tm = nullptr;
     int rc;
@@ -1108,15 +1112,16 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         // are resident at once
         const long long nitems = (long long)c->p.nz * ntx;
         if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
-#define GO(PP, PM, WT)                                                                                  \
+#define GO(PP, PM, WT) do { if (has_src) GO_S(PP, PM, WT, true); else GO_S(PP, PM, WT, false); } while (0)
+#define GO_S(PP, PM, WT, SRC)                                                                           \
     do {                                                                                                \
         using T = XSweepTile<PP>;                                                                       \
         static unsigned long long attr_done = 0;                                                        \
         static int per_sm[64];                                                                          \
         if (!(attr_done >> c->p.device & 1ull)) {                                                       \
-            if ((rc = set_smem(sweep_x<PP, PM, WT>, T::smem_bytes())) != PMW_OK) return rc;             \
+            if ((rc = set_smem(sweep_x<PP, PM, WT, SRC>, T::smem_bytes())) != PMW_OK) return rc;        \
             int nb = 0;                                                                                 \
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_x<PP, PM, WT>, 32 * T::WARPS, \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_x<PP, PM, WT, SRC>, 32 * T::WARPS, \
                                                                  T::smem_bytes()));                     \
             per_sm[c->p.device & 63] = std::max(nb, 1);                                                 \
             attr_done |= 1ull << c->p.device;                                                           \
@@ -1125,7 +1130,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
                                                   (nitems + T::WARPS - 1) / T::WARPS);                  \
         const int npush = a.push_epoch ? std::min(ncta, 8) : 0;                                         \
         const dim3 grid(ncta);                                                                          \
-        launch_ex(sweep_x<PP, PM, WT>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a, \
+        launch_ex(sweep_x<PP, PM, WT, SRC>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a, \
                   ntx, npush);                                                                          \
     } while (0)
 #define GO_P(PM, WT) do { if (P == 2) GO(2, PM, WT); else GO(3, PM, WT); } while (0)
@@ -1133,8 +1138,9 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         else      { if (write_tmp) GO_P(0, true); else GO_P(0, false); }
 #undef GO_P
 #undef GO
+#undef GO_S
         LAUNCHED(c, "sweep_x");
-    } else if (c->sweep_zt) {
+    } else if (c->sweep_zt && !has_src) {
         // transposing z sweep: items = (group of 4 columns, z tile); as many CTAs as are resident at once
         const int P = 2, LC = 64 * P - 10;
         if ((rc = get_tmap(c, pS, 4, 64 * P + 4, &tm, true)) != PMW_OK) return rc;
@@ -1169,10 +1175,13 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         if ((rc = get_tmap(c, pS, ZS_COLS, 1, &tm, true)) != PMW_OK) return rc;
         const dim3 grid((c->p.nx + ZS_COLS - 1) / ZS_COLS, (c->p.nz + a.lz - 1) / a.lz);
         if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
-#define GO(PM, WT) launch_ex(sweep_z<PM, WT>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a)
+#define GO_S(PM, WT, SRC) \
+    launch_ex(sweep_z<PM, WT, SRC>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a)
+#define GO(PM, WT) do { if (has_src) GO_S(PM, WT, true); else GO_S(PM, WT, false); } while (0)
         if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
         else      { if (write_tmp) GO(0, true); else GO(0, false); }
 #undef GO
+#undef GO_S
         LAUNCHED(c, "sweep_z");
     }
     if (e1) CU_TRY(cudaEventRecord(e1, c->stream));

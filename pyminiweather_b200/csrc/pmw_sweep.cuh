@@ -58,6 +58,8 @@ struct SweepArgs {
     unsigned long long* nbr_flags_right;
     unsigned int* push_counter;
     int dbg;
+    const double* src_w;  // HAS_SRC instantiations: [nz][nx] extra rho*w tendency of every stage (ic_type
+                          // "gravity", source.py:43-50); single periodic slab only
 };
 
 // Slab ring, fused x sweep: the first row of CTAs stores this slab's own six edge columns of S
@@ -157,11 +159,11 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_MINB
 #define PMW_XSWEEP_MINB 3
 #endif
-template <int P, int POW_MODE, bool WRITE_TMP>
+template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
 #ifdef PMW_XSWEEP_MAXNREG
 __global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
 #else
-__global__ void __launch_bounds__(32 * XSweepTile<P>::WARPS, PMW_XSWEEP_MINB)
+__global__ void __launch_bounds__(32 * XSweepTile<P>::WARPS, HAS_SRC ? 2 : PMW_XSWEEP_MINB)
 #endif
 sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int ntx, const int npush)
 {
@@ -262,7 +264,15 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                         const Pair in = lds2(rowS + v * FW + 64 * q + 2);
                         ia = in.a; ib = in.b;
                     }
-                    const double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                    double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                    if (HAS_SRC && v == WMOM) {
+                        // gravity-wave forcing (source.py:43-50) of the pair's cells; halo cells of T1 / T2
+                        // are periodic images, so they take the forcing of the cell they mirror
+                        int iw = i % nx;
+                        iw += (iw < 0) ? nx : 0;
+                        const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)it.k * nx + iw));
+                        ta += g.x; tb += g.y;
+                    }
                     const double2 x = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
                     if (ok) *reinterpret_cast<double2*>(dst + v * dvs) = x;  // generic store: shared or global
                     if (s == 2 && ok) {
@@ -541,8 +551,10 @@ struct ZStage {
 
     // Generic step (warp-uniform branches for walls): evaluate interface k from slots 0..3 and
     // finalise cell k-1 = init + dt*tendency.
+    // HAS_SRC: `src` is the gravity-wave forcing (source.py:43-50) of cell k-1.
+    template <bool HAS_SRC = false>
     __device__ __forceinline__ void step(const SweepArgs& a, int k, double dt_stage, const double (&init)[4],
-                                         double (&cell)[4])
+                                         double (&cell)[4], double src = 0.0)
     {
         const int nz = a.L.nz;
         const double* hd = a.hy.dens_cell;
@@ -574,7 +586,10 @@ struct ZStage {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             double t = (fprev[v] - f[v]) * a.inv_d;
-            if (v == WMOM) t = fma(-W[1][DENS], GRAV, t);  // hydrostatic source (interpolate.py:248-250)
+            if (v == WMOM) {
+                t = fma(-W[1][DENS], GRAV, t);  // hydrostatic source (interpolate.py:248-250)
+                if (HAS_SRC) t += src;
+            }
             cell[v] = fma(dt_stage, t, init[v]);
             fprev[v] = f[v];
         }
@@ -607,14 +622,17 @@ struct ZStage {
         for (int v = 0; v < 4; ++v) f[v] = g.f[v];
     }
     // cell k-1 (tap 1) from the fluxes through its two faces
-    template <int R0>
+    template <int R0, bool HAS_SRC = false>
     __device__ __forceinline__ void finish(const SweepArgs& a, const double (&f)[4], double dt_stage,
-                                           const double (&init)[4], double (&cell)[4])
+                                           const double (&init)[4], double (&cell)[4], double src = 0.0)
     {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             double t = (fprev[v] - f[v]) * a.inv_d;
-            if (v == WMOM) t = fma(-W[(R0 + 1) & 3][DENS], GRAV, t);
+            if (v == WMOM) {
+                t = fma(-W[(R0 + 1) & 3][DENS], GRAV, t);
+                if (HAS_SRC) t += src;
+            }
             cell[v] = fma(dt_stage, t, init[v]);
             fprev[v] = f[v];
         }
@@ -647,10 +665,11 @@ struct ZStream {  // per-warp constants of the state-row stream
 
 // One steady-state iteration at window rotation R: stage 1 at interface j, stage 2 at j-3, stage 3
 // at j-6; all interior, all cells valid.  Straight-line code: the three evaluations interleave.
-template <int R, int POW_MODE, bool WRITE_TMP>
+template <int R, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
 __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream& zs, ZStage<POW_MODE>& s1,
                                               ZStage<POW_MODE>& s2, ZStage<POW_MODE>& s3, int j, double* pout,
-                                              double* ptmp, bool col_ok, bool img_r, bool img_l)
+                                              double* ptmp, bool col_ok, bool img_r, bool img_l,
+                                              const double* psrc = nullptr)
 {
     __syncwarp();  // every lane is done with the rows of the previous iteration
     if (zs.lane == 0) zs.request(j + 1 + ZS_AHEAD);
@@ -684,9 +703,15 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
 #pragma unroll
         for (int v = 0; v < 4; ++v) ptmp[v * a.L.vstride] = s3.W[(R + 1) & 3][v];  // T2 of the cell
     }
-    s3.template finish<R>(a, f3, a.dt3, in3, c3);
-    s2.template finish<R>(a, f2, a.dt2, in2, c2);
-    s1.template finish<R + 1>(a, f1, a.dt1, s1.W[(R + 2) & 3], c1);
+    double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+    if (HAS_SRC) {  // psrc: this lane's column of source row j-7 (the cell stage 3 finishes)
+        g3 = __ldg(psrc);
+        g2 = __ldg(psrc + 3 * (long long)a.L.nx);  // stage 2 finishes cell j-4
+        g1 = __ldg(psrc + 6 * (long long)a.L.nx);  // stage 1 finishes cell j-1
+    }
+    s3.template finish<R, HAS_SRC>(a, f3, a.dt3, in3, c3, g3);
+    s2.template finish<R, HAS_SRC>(a, f2, a.dt2, in2, c2, g2);
+    s1.template finish<R + 1, HAS_SRC>(a, f1, a.dt1, s1.W[(R + 2) & 3], c1, g1);
     if (col_ok) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -703,7 +728,7 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
     }
 }
 
-template <int POW_MODE, bool WRITE_TMP>
+template <int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
 __global__ void __launch_bounds__(32)
 sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
 {
@@ -754,6 +779,11 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
     double* const ptmp0 = a.tmp + idx(a.L, 0, HS, min(i, nx - 1) + HS);
     const bool img_r = a.periodic && i < SWEEP_HALO, img_l = a.periodic && i >= nx - SWEEP_HALO;
 
+    // gravity-wave forcing of cell row m in this lane's column (rows beyond the domain: the cell is discarded)
+    auto zsrc = [&](int m) -> double {
+        if (!HAS_SRC) return 0.0;
+        return __ldg(a.src_w + (long long)min(max(m, 0), nz - 1) * nx + min(i, nx - 1));
+    };
     // steady iterations (all three stages active, every cell valid, no wall): js <= j <= je
     const int js = max(lo3 + 7, 7), je = min(hi1, nz - 2);
     int j = lo1;
@@ -762,6 +792,15 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
             double* po = pout0 + (long long)(j - 7) * a.L.pitch;
             double* pt = ptmp0 + (long long)(j - 7) * a.L.pitch;
             const int p = a.L.pitch;
+            if (HAS_SRC) {
+                const double* ps = a.src_w + (long long)(j - 7) * nx + min(i, nx - 1);
+                zsweep_steady<0, POW_MODE, WRITE_TMP, true>(a, zs, s1, s2, s3, j, po, pt, col_ok, img_r, img_l, ps);
+                zsweep_steady<1, POW_MODE, WRITE_TMP, true>(a, zs, s1, s2, s3, j + 1, po + p, pt + p, col_ok, img_r, img_l, ps + nx);
+                zsweep_steady<2, POW_MODE, WRITE_TMP, true>(a, zs, s1, s2, s3, j + 2, po + 2 * p, pt + 2 * p, col_ok, img_r, img_l, ps + 2 * nx);
+                zsweep_steady<3, POW_MODE, WRITE_TMP, true>(a, zs, s1, s2, s3, j + 3, po + 3 * p, pt + 3 * p, col_ok, img_r, img_l, ps + 3 * nx);
+                j += 4;
+                continue;
+            }
             zsweep_steady<0, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j, po, pt, col_ok, img_r, img_l);
             zsweep_steady<1, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j + 1, po + p, pt + p, col_ok, img_r, img_l);
             zsweep_steady<2, POW_MODE, WRITE_TMP>(a, zs, s1, s2, s3, j + 2, po + 2 * p, pt + 2 * p, col_ok, img_r, img_l);
@@ -790,7 +829,7 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
         if (k3 >= lo3 && k3 <= hi3) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) in3[v] = (k3 > lo3) ? zs.row(k3 - 1)[v * ZS_COLS] : 0.0;
-            s3.step(a, k3, a.dt3, in3, c3);
+            s3.template step<HAS_SRC>(a, k3, a.dt3, in3, c3, zsrc(k3 - 1));
             if (k3 > lo3 && col_ok) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -805,9 +844,9 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
         if (k2 >= lo2 && k2 <= hi2) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) in2[v] = (k2 > lo2) ? zs.row(k2 - 1)[v * ZS_COLS] : 0.0;
-            s2.step(a, k2, a.dt2, in2, c2);
+            s2.template step<HAS_SRC>(a, k2, a.dt2, in2, c2, zsrc(k2 - 1));
         }
-        if (k1 <= hi1) s1.step(a, k1, a.dt1, s1.W[1], c1);
+        if (k1 <= hi1) s1.template step<HAS_SRC>(a, k1, a.dt1, s1.W[1], c1, zsrc(k1 - 1));
         s3.push(c2);
         s2.push(c1);
         ++j;

@@ -345,6 +345,28 @@ def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("nx,nz,tune", [(100, 50, {}), (256, 128, dict(sweep_lz=40)), (130, 33, dict(sweep_lz=9))])
+def test_fused_sweeps_with_gravity_source_bitwise_equal_stage_by_stage(nx, nz, tune):
+    """ic_type 'gravity': the constant rho*w forcing (source.py:43-50) applied in registers by the fused
+    sweeps (HAS_SRC instantiations; recomputed halo cells take the forcing of the cell they mirror)
+    against the stage-by-stage kernels, bit for bit, and against the NumPy oracle."""
+    p, case = new_case(nx, nz, "gravity")
+    src = case.source_w
+    assert np.count_nonzero(src) > 0
+    a, b = solver_for(case, fuse=0), solver_for(case, fuse=1, **tune)
+    a.set_source_w(src); b.set_source_w(src)
+    for n in (1, 6):
+        a.evolve(n); b.evolve(n)
+        ra, rb = a.download(STATE), b.download(STATE)
+        assert np.array_equal(ra[:, 2:-2, :], rb[:, 2:-2, :])
+        assert np.array_equal(interior(a.download(TMP)), interior(b.download(TMP)))
+    assert b.launch_count < a.launch_count     # really one kernel per sweep
+    for _ in range(7):
+        no.evolve(case)
+    assert worst_rel_l2(rb, case.state) <= STATE_TOL
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("zt", [1, 0])
 def test_fused_sweeps_thermal_walls_vs_oracle(zt):
     """Thermal bubble 100x50 x 100 steps through the fused sweeps against the golden reference state."""
