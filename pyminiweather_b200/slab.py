@@ -38,13 +38,17 @@ class SlabMesh:
         self.x0 = rank * self.nx_local * self.dx
         self._cache = {}
 
+    def get_axes_int_ext(self):
+        """1-D axes of the slab's array columns / rows (what the device-side init takes)."""
+        hs, n = self.hs, self.nx_local
+        # same spacing as linspace(-hs*dx, (nx+hs)*dx, nx+2hs, endpoint=False), shifted
+        x = self.x0 + (np.arange(n + 2 * hs) - hs) * self.dx
+        z = np.linspace(-hs * self.dz, (self.nz + hs) * self.dz, self.nz + 2 * hs, endpoint=False)
+        return x, z
+
     def get_mesh_int_ext(self):
         if "ie" not in self._cache:
-            hs, n = self.hs, self.nx_local
-            # same spacing as linspace(-hs*dx, (nx+hs)*dx, nx+2hs, endpoint=False), shifted
-            x = self.x0 + (np.arange(n + 2 * hs) - hs) * self.dx
-            z = np.linspace(-hs * self.dz, (self.nz + hs) * self.dz, self.nz + 2 * hs, endpoint=False)
-            self._cache["ie"] = np.meshgrid(x, z)
+            self._cache["ie"] = np.meshgrid(*self.get_axes_int_ext())
         return self._cache["ie"]
 
     def get_mesh_vertical_cell_edges(self):

@@ -347,3 +347,29 @@ def test_evolve_from_device_init_vs_oracle():
             no.evolve(case)
         assert worst_rel_l2(f.state, case.state) <= 1e-11, ic
         f.close()
+
+
+def test_device_init_of_slabs_matches_the_whole_domain():
+    """pmw_init_state on x-slab contexts (each given its own part of the x axis, SlabMesh) against
+    the columns of the whole-domain device init."""
+    from pyminiweather_b200.engine import DeviceSolver
+    from pyminiweather_b200.ics.initial_conditions import device_spec
+    from pyminiweather_b200.mesh import MeshData
+    from pyminiweather_b200.slab import SlabMesh
+    nx, nz, world = 192, 48, 3
+    p = make_params(nx, nz, "collision")
+    bubbles, wind, bv0 = device_spec("collision", p["xlen"])
+    whole = DeviceSolver(nx, nz, p["dx"], p["dz"], p["dt"])
+    whole.init_state(bubbles, wind, bv0, *MeshData(p).get_axes_int_ext())
+    want = whole.download(0)
+    assert np.linalg.norm(want[3]) > 1.0
+    nxl = nx // world
+    for r in range(world):
+        ps = dict(p, nx=nxl)
+        s = DeviceSolver(nxl, nz, p["dx"], p["dz"], p["dt"], periodic_x=False)
+        s.init_state(bubbles, wind, bv0, *SlabMesh(ps, r, world).get_axes_int_ext())
+        got, ref = s.download(0), want[:, :, r * nxl: (r + 1) * nxl + 4]
+        assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(want), r
+        assert np.array_equal(got, s.download(1))
+        s.close()
+    whole.close()
