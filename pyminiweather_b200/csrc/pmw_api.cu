@@ -1022,7 +1022,7 @@ static bool fuse_ok(const pmw_ctx* c)
 
 // Rows per z-sweep segment: a warp (32 columns x lz rows) is the unit of work and every SM holds
 // kZWarps of them; pick the segment count that fills whole waves with the least recomputation.
-static const int kZWarpsPerSM = 8;
+static const int kZWarpsPerSM = PMW_ZSWEEP_MINB;
 static int pick_sweep_lz(const pmw_ctx* c)
 {
     if (c->sweep_lz) return std::min(c->sweep_lz, c->p.nz);

@@ -159,6 +159,12 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_MINB
 #define PMW_XSWEEP_MINB 3
 #endif
+#ifndef PMW_XSWEEP_ITER
+#define PMW_XSWEEP_ITER 1  // 1: walk the item list incrementally (no integer division per item)
+#endif
+#ifndef PMW_XSWEEP_UPD
+#define PMW_XSWEEP_UPD 1  // 1: update block of a pass restructured (see the pass body): x sweep 56.6 -> 53.2 us at 2048x1024
+#endif
 template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
 #ifdef PMW_XSWEEP_MAXNREG
 __global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
@@ -198,8 +204,23 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     if (a.push_epoch && blockIdx.x < npush) push_halo6_role(a, npush);
 
     const unsigned long long pol = l2_policy(1);
+#if PMW_XSWEEP_ITER == 1
+    // Items without a division per item: (tile column index, row) of the NEXT item advance by the
+    // constant stride nwarps = dq * nz + dr.
+    const int dq = nwarps / nz, dr = nwarps - dq * nz;
+    int nc = w / nz, nk = w - nc * nz;
+    auto make_item = [&](int cidx, int k) {
+        XItem it;
+        it.k = k;
+        it.tx = !a.edge_last ? cidx : ((cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1));
+        it.c0 = it.tx * T::LC;
+        return it;
+    };
+    auto request = [&](const XItem& it, int buf) {  // lane 0: start the load of the item's state row
+#else
     auto request = [&](int n, int buf) {  // lane 0: start the load of item n's state row
         const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
+#endif
         if (a.wait_epoch && !(a.dbg & 2)) {
             if (it.c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
             if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
@@ -209,14 +230,28 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         // map column 0 is interior column -6 (array column -4)
         tma_load_3d(sS + buf * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
     };
+#if PMW_XSWEEP_ITER == 1
+    XItem nxt = make_item(nc, nk);
+    if (w < nitems && lane == 0) request(nxt, 0);
+#else
     if (w < nitems && lane == 0) request(w, 0);
+#endif
     const int src_lane = (lane + 1) & 31;
     int buf = 0;
     unsigned phase = 0;  // bit b: parity of the next completion of bars[b]
 #pragma unroll 1
     for (int n = w; n < nitems; n += nwarps) {
+#if PMW_XSWEEP_ITER == 1
+        const XItem it = nxt;
+        nk += dr;
+        nc += dq;
+        if (nk >= nz) { nk -= nz; ++nc; }
+        nxt = make_item(nc, nk);
+        if (n + nwarps < nitems && lane == 0) request(nxt, buf ^ 1);
+#else
         const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
         if (n + nwarps < nitems && lane == 0) request(n + nwarps, buf ^ 1);
+#endif
         const IfaceBg bg = bg_x(a.hy, it.k + HS);
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
@@ -254,6 +289,52 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 // stage 1 -> T1, stage 2 -> T2 (column t), stage 3 -> HBM
                 double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + s * T::S_ELEMS + 64 * q + 2;
                 const long long dvs = (s == 2) ? a.L.vstride : (long long)FW;
+#if PMW_XSWEEP_UPD == 1
+                // All four variables' updates as ONE straight-line block (eight independent FP64 chains, the
+                // four shuffles in flight together), then the stores; the rare extra stores (periodic images
+                // of the edge columns, state_tmp) sit behind a single branch per pass instead of one per
+                // variable, which used to split the block and serialise the variables.
+                double2 xv[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const double give = (lane == 0) ? keep[v] : f0[v];
+                    const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
+                    keep[v] = f0[v];
+                    double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
+                    if (s != 0) {
+                        const Pair in = lds2(rowS + v * FW + 64 * q + 2);
+                        ia = in.a; ib = in.b;
+                    }
+                    double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                    if (HAS_SRC && v == WMOM) {
+                        int iw = i % nx;
+                        iw += (iw < 0) ? nx : 0;
+                        const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)it.k * nx + iw));
+                        ta += g.x; tb += g.y;
+                    }
+                    xv[v] = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
+                }
+                if (ok) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs) = xv[v];  // generic store: shared or global
+                }
+                if (s == 2 && ok) {
+                    if (a.periodic && (i < SWEEP_HALO || i >= nx - SWEEP_HALO)) {
+                        const long long img = (i < SWEEP_HALO) ? nx : -nx;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs + img) = xv[v];
+                        if (i < SWEEP_HALO && i >= nx - SWEEP_HALO) {  // a domain narrower than 12 columns: both images
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs - nx) = xv[v];
+                        }
+                    }
+                    if (WRITE_TMP) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            *reinterpret_cast<double2*>(dst + v * dvs + tmp_off) = make_double2(t2[v], t3[v]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const double give = (lane == 0) ? keep[v] : f0[v];
@@ -283,6 +364,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                         if (WRITE_TMP) *reinterpret_cast<double2*>(dst + v * dvs + tmp_off) = make_double2(t2[v], t3[v]);
                     }
                 }
+#endif
             }
             __syncwarp();
             src = rowT + s * T::S_ELEMS;
@@ -728,8 +810,15 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
     }
 }
 
+#ifndef PMW_ZSWEEP_MINB
+#define PMW_ZSWEEP_MINB 8  // resident warps (= CTAs) per SM the register allocation aims at: 8 -> 255 registers
+#endif
 template <int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
+#ifdef PMW_ZSWEEP_MAXNREG
+__global__ void __maxnreg__(PMW_ZSWEEP_MAXNREG)
+#else
 __global__ void __launch_bounds__(32)
+#endif
 sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
