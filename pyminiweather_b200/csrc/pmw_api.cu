@@ -793,6 +793,8 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.hv_coeff = -HV_BETA * d / (16 * c->p.dt);
     a.inv_d = 1.0 / d;
     a.dt_stage = dt_stage;
+    a.cd = dt_stage * a.inv_d;
+    a.cg = dt_stage * GRAV;
     a.write_xhalo = (write_xhalo && c->p.periodic_x) ? 1 : 0;
     if (c->peers && fuse_bc_z && direction == PMW_DIR_X) {
         // Slab ring, fused path: this x stage first pushes its own edge columns of `forcing` into the
@@ -1061,6 +1063,9 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     a.dt1 = dt / 3;
     a.dt2 = dt / 2;
     a.dt3 = dt / 1;
+    // the same products launch_stage forms for the stage-by-stage path (bit-identical results)
+    a.cd1 = a.dt1 * a.inv_d; a.cd2 = a.dt2 * a.inv_d; a.cd3 = a.dt3 * a.inv_d;
+    a.cg1 = a.dt1 * GRAV;    a.cg2 = a.dt2 * GRAV;    a.cg3 = a.dt3 * GRAV;
     a.periodic = c->p.periodic_x ? 1 : 0;
     a.lz = 0;
     a.tile_x0 = a.tile_y0 = 0;

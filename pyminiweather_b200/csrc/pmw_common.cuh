@@ -93,7 +93,24 @@ struct StageArgs {
     // Chunked sweeps: this launch covers only the tile columns (z stages) / tile rows (x stages)
     // starting at these offsets; the grid dimensions give the extent.
     int tile_x0, tile_y0;
+    double cd, cg;  // dt_stage/d and dt_stage*grav (cell_update)
 };
+
+// The stage update of one cell, out = init + dt_stage * tend with
+//     tend = -(F_hi - F_lo)/d  [- rho'*grav: z sweeps, rho*w]  [+ src: gravity-wave forcing, rho*w]
+// (interpolate.py:208-215,238-250, source.py:43-50, step.py:80-82), folded into fused multiply-adds
+// with the host-computed factors cd = dt_stage/d and cg = dt_stage*grav: one multiplication per cell
+// and variable fewer than tend-then-update, same value to rounding.  EVERY kernel updates cells
+// through this function, which is what keeps the kernel variants bit-identical to each other.
+template <bool HYDRO_SRC, bool EXTRA_SRC>
+__device__ __forceinline__ double cell_update(double f_lo, double f_hi, double init, double cd, double cg,
+                                              double dens, double dt_stage, double src)
+{
+    double base = init;
+    if (HYDRO_SRC) base = fma(-cg, dens, base);
+    if (EXTRA_SRC) base = fma(dt_stage, src, base);
+    return fma(cd, f_lo - f_hi, base);
+}
 
 __device__ __forceinline__ unsigned long long l2_policy(int kind)
 {

@@ -96,10 +96,14 @@ __device__ __forceinline__ void stage_x_direct_cell(const StageArgs& a, int i, i
     interface_flux<false, POW_MODE>(s[1], s[2], s[3], s[4], bg, a.hv_coeff, false, fr);
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        double tend = (fl[v] - fr[v]) * a.inv_d;
-        if (v == WMOM && a.src_w) tend += __ldg(a.src_w + (long long)k * a.L.nx + i);
         const double ini = (a.init == a.forcing) ? s[2][v] : __ldg(a.init + idx(a.L, v, k + HS, i + HS));
-        store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
+        double x;
+        if (v == WMOM && a.src_w)
+            x = cell_update<false, true>(fl[v], fr[v], ini, a.cd, a.cg, 0.0, a.dt_stage,
+                                         __ldg(a.src_w + (long long)k * a.L.nx + i));
+        else
+            x = cell_update<false, false>(fl[v], fr[v], ini, a.cd, a.cg, 0.0, a.dt_stage, 0.0);
+        store_cell(a, v, k, i, x);
     }
 }
 
@@ -141,13 +145,18 @@ __device__ __forceinline__ void stage_z_direct_cell(const StageArgs& a, int i, i
                                    k + 1 == nz, ft);
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        double tend = (fb[v] - ft[v]) * a.inv_d;
-        if (v == WMOM) {
-            tend = fma(-s[2][DENS], GRAV, tend);  // interpolate.py:248-250
-            if (a.src_w) tend += __ldg(a.src_w + (long long)k * a.L.nx + i);
-        }
         const double ini = (a.init == a.forcing) ? s[2][v] : __ldg(a.init + idx(a.L, v, k + HS, i + HS));
-        store_cell(a, v, k, i, fma(a.dt_stage, tend, ini));
+        double x;
+        if (v == WMOM) {  // hydrostatic source on the cell's rho' (interpolate.py:248-250)
+            if (a.src_w)
+                x = cell_update<true, true>(fb[v], ft[v], ini, a.cd, a.cg, s[2][DENS], a.dt_stage,
+                                            __ldg(a.src_w + (long long)k * a.L.nx + i));
+            else
+                x = cell_update<true, false>(fb[v], ft[v], ini, a.cd, a.cg, s[2][DENS], a.dt_stage, 0.0);
+        } else {
+            x = cell_update<false, false>(fb[v], ft[v], ini, a.cd, a.cg, 0.0, a.dt_stage, 0.0);
+        }
+        store_cell(a, v, k, i, x);
     }
 }
 

@@ -60,6 +60,8 @@ struct SweepArgs {
     int dbg;
     const double* src_w;  // HAS_SRC instantiations: [nz][nx] extra rho*w tendency of every stage (ic_type
                           // "gravity", source.py:43-50); single periodic slab only
+    double cd1, cd2, cd3;  // dt_s / d    per stage (cell_update, pmw_common.cuh)
+    double cg1, cg2, cg3;  // dt_s * grav per stage
 };
 
 // Slab ring, fused x sweep: the first row of CTAs stores this slab's own six edge columns of S
@@ -162,9 +164,6 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_ITER
 #define PMW_XSWEEP_ITER 1  // 1: walk the item list incrementally (no integer division per item)
 #endif
-#ifndef PMW_XSWEEP_UPD
-#define PMW_XSWEEP_UPD 1  // 1: update block of a pass restructured (see the pass body): x sweep 56.6 -> 53.2 us at 2048x1024
-#endif
 template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
 #ifdef PMW_XSWEEP_MAXNREG
 __global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
@@ -265,7 +264,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         phase ^= 1u << buf;
 
         const double* src = rowS;  // forcing row of the stage (+ 2*lane)
-        double dts = a.dt1;
+        double dts = a.dt1, cds = a.cd1;
         int tlo = 2, thi = 64 * P;
 #pragma unroll 1
         for (int s = 0; s < 3; ++s) {
@@ -289,7 +288,6 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 // stage 1 -> T1, stage 2 -> T2 (column t), stage 3 -> HBM
                 double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + s * T::S_ELEMS + 64 * q + 2;
                 const long long dvs = (s == 2) ? a.L.vstride : (long long)FW;
-#if PMW_XSWEEP_UPD == 1
                 // All four variables' updates as ONE straight-line block (eight independent FP64 chains, the
                 // four shuffles in flight together), then the stores; the rare extra stores (periodic images
                 // of the edge columns, state_tmp) sit behind a single branch per pass instead of one per
@@ -305,14 +303,18 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                         const Pair in = lds2(rowS + v * FW + 64 * q + 2);
                         ia = in.a; ib = in.b;
                     }
-                    double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
                     if (HAS_SRC && v == WMOM) {
+                        // gravity-wave forcing (source.py:43-50) of the pair's cells; halo cells of T1 / T2
+                        // are periodic images, so they take the forcing of the cell they mirror
                         int iw = i % nx;
                         iw += (iw < 0) ? nx : 0;
                         const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)it.k * nx + iw));
-                        ta += g.x; tb += g.y;
+                        xv[v] = make_double2(cell_update<false, true>(f0[v], f1[v], ia, cds, 0.0, 0.0, dts, g.x),
+                                             cell_update<false, true>(f1[v], fr, ib, cds, 0.0, 0.0, dts, g.y));
+                    } else {
+                        xv[v] = make_double2(cell_update<false, false>(f0[v], f1[v], ia, cds, 0.0, 0.0, dts, 0.0),
+                                             cell_update<false, false>(f1[v], fr, ib, cds, 0.0, 0.0, dts, 0.0));
                     }
-                    xv[v] = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
                 }
                 if (ok) {
 #pragma unroll
@@ -334,41 +336,11 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                             *reinterpret_cast<double2*>(dst + v * dvs + tmp_off) = make_double2(t2[v], t3[v]);
                     }
                 }
-#else
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const double give = (lane == 0) ? keep[v] : f0[v];
-                    const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
-                    keep[v] = f0[v];
-                    double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
-                    if (s != 0) {
-                        const Pair in = lds2(rowS + v * FW + 64 * q + 2);
-                        ia = in.a; ib = in.b;
-                    }
-                    double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
-                    if (HAS_SRC && v == WMOM) {
-                        // gravity-wave forcing (source.py:43-50) of the pair's cells; halo cells of T1 / T2
-                        // are periodic images, so they take the forcing of the cell they mirror
-                        int iw = i % nx;
-                        iw += (iw < 0) ? nx : 0;
-                        const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)it.k * nx + iw));
-                        ta += g.x; tb += g.y;
-                    }
-                    const double2 x = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
-                    if (ok) *reinterpret_cast<double2*>(dst + v * dvs) = x;  // generic store: shared or global
-                    if (s == 2 && ok) {
-                        if (a.periodic) {
-                            if (i < SWEEP_HALO) *reinterpret_cast<double2*>(dst + v * dvs + nx) = x;
-                            if (i >= nx - SWEEP_HALO) *reinterpret_cast<double2*>(dst + v * dvs - nx) = x;
-                        }
-                        if (WRITE_TMP) *reinterpret_cast<double2*>(dst + v * dvs + tmp_off) = make_double2(t2[v], t3[v]);
-                    }
-                }
-#endif
             }
             __syncwarp();
             src = rowT + s * T::S_ELEMS;
             dts = (s == 0) ? a.dt2 : a.dt3;
+            cds = (s == 0) ? a.cd2 : a.cd3;
             tlo += 2;
             thi -= 2;
         }
@@ -503,7 +475,7 @@ sweep_zt(const __grid_constant__ CUtensorMap tm_box, const SweepArgs a, const in
         double* const rowT = sT + 2 * lane;
         const double* src = rowS;
         int vs = FW;
-        double dts = a.dt1;
+        double dts = a.dt1, cds = a.cd1, cgs = a.cg1;
         int tlo = 2, thi = 64 * P;
 #pragma unroll 1
         for (int s = 0; s < 3; ++s) {
@@ -567,12 +539,14 @@ sweep_zt(const __grid_constant__ CUtensorMap tm_box, const SweepArgs a, const in
                         const Pair in = lds2(rowS + v * FW + 64 * q + 2);
                         ia = in.a; ib = in.b;
                     }
-                    double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
-                    if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250): the cells are taps 2 and 3
-                        ta = fma(-t2[DENS], GRAV, ta);
-                        tb = fma(-t3[DENS], GRAV, tb);
-                    }
-                    if (ok) *reinterpret_cast<double2*>(dst + v * dvs) = make_double2(fma(dts, ta, ia), fma(dts, tb, ib));
+                    double2 x;
+                    if (v == WMOM)  // hydrostatic source (interpolate.py:248-250): the cells are taps 2 and 3
+                        x = make_double2(cell_update<true, false>(f0[v], f1[v], ia, cds, cgs, t2[DENS], dts, 0.0),
+                                         cell_update<true, false>(f1[v], fr, ib, cds, cgs, t3[DENS], dts, 0.0));
+                    else
+                        x = make_double2(cell_update<false, false>(f0[v], f1[v], ia, cds, cgs, 0.0, dts, 0.0),
+                                         cell_update<false, false>(f1[v], fr, ib, cds, cgs, 0.0, dts, 0.0));
+                    if (ok) *reinterpret_cast<double2*>(dst + v * dvs) = x;
                 }
             }
             __syncwarp();
@@ -580,6 +554,8 @@ sweep_zt(const __grid_constant__ CUtensorMap tm_box, const SweepArgs a, const in
             src = rowT + 2 * s;
             vs = TW;
             dts = (s == 0) ? a.dt2 : a.dt3;
+            cds = (s == 0) ? a.cd2 : a.cd3;
+            cgs = (s == 0) ? a.cg2 : a.cg3;
             tlo += 2;
             thi -= 2;
         }
@@ -635,8 +611,8 @@ struct ZStage {
     // finalise cell k-1 = init + dt*tendency.
     // HAS_SRC: `src` is the gravity-wave forcing (source.py:43-50) of cell k-1.
     template <bool HAS_SRC = false>
-    __device__ __forceinline__ void step(const SweepArgs& a, int k, double dt_stage, const double (&init)[4],
-                                         double (&cell)[4], double src = 0.0)
+    __device__ __forceinline__ void step(const SweepArgs& a, int k, double dt_stage, double cd, double cg,
+                                         const double (&init)[4], double (&cell)[4], double src = 0.0)
     {
         const int nz = a.L.nz;
         const double* hd = a.hy.dens_cell;
@@ -667,12 +643,10 @@ struct ZStage {
         interface_flux<true, POW_MODE>(W[0], W[1], W[2], W[3], bg, a.hv_coeff, wall, f);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            double t = (fprev[v] - f[v]) * a.inv_d;
-            if (v == WMOM) {
-                t = fma(-W[1][DENS], GRAV, t);  // hydrostatic source (interpolate.py:248-250)
-                if (HAS_SRC) t += src;
-            }
-            cell[v] = fma(dt_stage, t, init[v]);
+            if (v == WMOM)  // hydrostatic source on the cell's rho' (interpolate.py:248-250)
+                cell[v] = cell_update<true, HAS_SRC>(fprev[v], f[v], init[v], cd, cg, W[1][DENS], dt_stage, src);
+            else
+                cell[v] = cell_update<false, false>(fprev[v], f[v], init[v], cd, cg, 0.0, dt_stage, 0.0);
             fprev[v] = f[v];
         }
     }
@@ -705,17 +679,15 @@ struct ZStage {
     }
     // cell k-1 (tap 1) from the fluxes through its two faces
     template <int R0, bool HAS_SRC = false>
-    __device__ __forceinline__ void finish(const SweepArgs& a, const double (&f)[4], double dt_stage,
-                                           const double (&init)[4], double (&cell)[4], double src = 0.0)
+    __device__ __forceinline__ void finish(const SweepArgs& a, const double (&f)[4], double dt_stage, double cd,
+                                           double cg, const double (&init)[4], double (&cell)[4], double src = 0.0)
     {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            double t = (fprev[v] - f[v]) * a.inv_d;
-            if (v == WMOM) {
-                t = fma(-W[(R0 + 1) & 3][DENS], GRAV, t);
-                if (HAS_SRC) t += src;
-            }
-            cell[v] = fma(dt_stage, t, init[v]);
+            if (v == WMOM)
+                cell[v] = cell_update<true, HAS_SRC>(fprev[v], f[v], init[v], cd, cg, W[(R0 + 1) & 3][DENS], dt_stage, src);
+            else
+                cell[v] = cell_update<false, false>(fprev[v], f[v], init[v], cd, cg, 0.0, dt_stage, 0.0);
             fprev[v] = f[v];
         }
     }
@@ -791,9 +763,9 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
         g2 = __ldg(psrc + 3 * (long long)a.L.nx);  // stage 2 finishes cell j-4
         g1 = __ldg(psrc + 6 * (long long)a.L.nx);  // stage 1 finishes cell j-1
     }
-    s3.template finish<R, HAS_SRC>(a, f3, a.dt3, in3, c3, g3);
-    s2.template finish<R, HAS_SRC>(a, f2, a.dt2, in2, c2, g2);
-    s1.template finish<R + 1, HAS_SRC>(a, f1, a.dt1, s1.W[(R + 2) & 3], c1, g1);
+    s3.template finish<R, HAS_SRC>(a, f3, a.dt3, a.cd3, a.cg3, in3, c3, g3);
+    s2.template finish<R, HAS_SRC>(a, f2, a.dt2, a.cd2, a.cg2, in2, c2, g2);
+    s1.template finish<R + 1, HAS_SRC>(a, f1, a.dt1, a.cd1, a.cg1, s1.W[(R + 2) & 3], c1, g1);
     if (col_ok) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -918,7 +890,7 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
         if (k3 >= lo3 && k3 <= hi3) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) in3[v] = (k3 > lo3) ? zs.row(k3 - 1)[v * ZS_COLS] : 0.0;
-            s3.template step<HAS_SRC>(a, k3, a.dt3, in3, c3, zsrc(k3 - 1));
+            s3.template step<HAS_SRC>(a, k3, a.dt3, a.cd3, a.cg3, in3, c3, zsrc(k3 - 1));
             if (k3 > lo3 && col_ok) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -933,9 +905,9 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
         if (k2 >= lo2 && k2 <= hi2) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) in2[v] = (k2 > lo2) ? zs.row(k2 - 1)[v * ZS_COLS] : 0.0;
-            s2.template step<HAS_SRC>(a, k2, a.dt2, in2, c2, zsrc(k2 - 1));
+            s2.template step<HAS_SRC>(a, k2, a.dt2, a.cd2, a.cg2, in2, c2, zsrc(k2 - 1));
         }
-        if (k1 <= hi1) s1.template step<HAS_SRC>(a, k1, a.dt1, s1.W[1], c1, zsrc(k1 - 1));
+        if (k1 <= hi1) s1.template step<HAS_SRC>(a, k1, a.dt1, a.cd1, a.cg1, s1.W[1], c1, zsrc(k1 - 1));
         s3.push(c2);
         s2.push(c1);
         ++j;

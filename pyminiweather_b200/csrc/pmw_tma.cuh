@@ -251,13 +251,15 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
                 } else {
                     ia = t2[v]; ib = t3[v];
                 }
-                double ta = (f0[v] - f1[v]) * a.inv_d, tb = (f1[v] - fr) * a.inv_d;
+                double xa, xb;
                 if (HAS_SRC && v == WMOM) {  // gravity-wave forcing (source.py:43-50)
                     const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)k * nx + i));
-                    ta += g.x; tb += g.y;
+                    xa = cell_update<false, true>(f0[v], f1[v], ia, a.cd, a.cg, 0.0, a.dt_stage, g.x);
+                    xb = cell_update<false, true>(f1[v], fr, ib, a.cd, a.cg, 0.0, a.dt_stage, g.y);
+                } else {
+                    xa = cell_update<false, false>(f0[v], f1[v], ia, a.cd, a.cg, 0.0, a.dt_stage, 0.0);
+                    xb = cell_update<false, false>(f1[v], fr, ib, a.cd, a.cg, 0.0, a.dt_stage, 0.0);
                 }
-                const double xa = fma(a.dt_stage, ta, ia);
-                const double xb = fma(a.dt_stage, tb, ib);
                 store_pair(a, po + 64 * q, v * a.L.vstride, edge, i, xa, xb, pol_out);
             }
         }
@@ -425,22 +427,26 @@ stage_z_tma(const __grid_constant__ CUtensorMap tm_forcing, const StageArgs a)
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 const Pair up = lds2(xr + v * rstride);
-                double ta = (fa[v] - up.a) * a.inv_d;
-                double tb = (fb[v] - up.b) * a.inv_d;
-                if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250); cell kf is tap 2
-                    ta = fma(-a2[DENS], GRAV, ta);
-                    tb = fma(-b2[DENS], GRAV, tb);
-                    if (HAS_SRC) {  // gravity-wave forcing (source.py:43-50)
-                        const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)kf * nx + i));
-                        ta += g.x; tb += g.y;
-                    }
-                }
                 double ia = a2[v], ib = b2[v];
                 if (HAS_INIT) {
                     const Pair in = lds2(sIn + (((p & 1) * NVAR + v) * W + warp) * TC + col);
                     ia = in.a; ib = in.b;
                 }
-                store_pair(a, po, v * a.L.vstride, edge, i, fma(a.dt_stage, ta, ia), fma(a.dt_stage, tb, ib), pol_out);
+                double xa, xb;
+                if (v == WMOM) {  // hydrostatic source (interpolate.py:248-250); cell kf is tap 2
+                    if (HAS_SRC) {  // gravity-wave forcing (source.py:43-50)
+                        const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)kf * nx + i));
+                        xa = cell_update<true, true>(fa[v], up.a, ia, a.cd, a.cg, a2[DENS], a.dt_stage, g.x);
+                        xb = cell_update<true, true>(fb[v], up.b, ib, a.cd, a.cg, b2[DENS], a.dt_stage, g.y);
+                    } else {
+                        xa = cell_update<true, false>(fa[v], up.a, ia, a.cd, a.cg, a2[DENS], a.dt_stage, 0.0);
+                        xb = cell_update<true, false>(fb[v], up.b, ib, a.cd, a.cg, b2[DENS], a.dt_stage, 0.0);
+                    }
+                } else {
+                    xa = cell_update<false, false>(fa[v], up.a, ia, a.cd, a.cg, 0.0, a.dt_stage, 0.0);
+                    xb = cell_update<false, false>(fb[v], up.b, ib, a.cd, a.cg, 0.0, a.dt_stage, 0.0);
+                }
+                store_pair(a, po, v * a.L.vstride, edge, i, xa, xb, pol_out);
             }
         }
         if (HAS_INIT) {  // refill the ring slot just consumed with the pass two below (or an empty group)
