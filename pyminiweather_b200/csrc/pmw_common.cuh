@@ -144,26 +144,26 @@ __device__ __forceinline__ void push_halo_role(const StageArgs& a)
 }
 
 // ---------------------------------------------------------------------------------
-// (1+e)^gamma - 1 on |e| <= 1/8: degree-12 polynomial (Chebyshev-node interpolant of
-// ((1+e)^gamma-1)/e, truncation error 7e-20, evaluated as two interleaved Horner chains in
-// e^2; absolute error <= 4e-17 measured against mpmath).  Used by PMW_POW_BACKGROUND.
+// (1+e)^gamma - 1 = e * g(e) on |e| <= 1/8, g the degree-10 interpolant of ((1+e)^gamma-1)/e at
+// Chebyshev nodes (tools/pow_poly.py generates the coefficients and checks them against mpmath:
+// 3.1e-17 absolute error in exact arithmetic with these double coefficients, 6.2e-17 as evaluated --
+// below half an ulp of the pressure; degrees 11 and 12 are no better once their coefficients are
+// rounded to double, degree 9 is 3.7e-16).  Two interleaved Horner chains in e^2.  PMW_POW_BACKGROUND.
 // ---------------------------------------------------------------------------------
 // The coefficients live in the constant bank so that they are direct operands of the DFMAs (as
 // immediates every one of them costs two UMOVs per use: 17 % of the instructions of a fused sweep).
-__constant__ double kPow1p[13] = {
+__constant__ double kPow1p[11] = {
     0x1.6678ae3cb2859p+0,    // c0
-    0x1.1efa23f1c08bdp-2,    // c1
-    -0x1.caf32d76b8de6p-5,   // c2
-    0x1.6f188e3a61d00p-6,    // c3
-    -0x1.7dbd21dc9b33fp-7,   // c4
-    0x1.ca0d1259f841dp-8,    // c5
-    -0x1.2cfc9a56ff6c7p-8,   // c6
-    0x1.a55c83fc9dc65p-9,    // c7
-    -0x1.34fc42d60dfbcp-9,   // c8
-    0x1.d56fc4d94646ap-10,   // c9
-    -0x1.6efd8124188fdp-10,  // c10
-    0x1.300687b793e42p-10,   // c11
-    -0x1.f04c6e36150e8p-11,  // c12
+    0x1.1efa23f1c098cp-2,    // c1
+    -0x1.caf32d76b9336p-5,   // c2
+    0x1.6f188e364e3d0p-6,    // c3
+    -0x1.7dbd21d5f3b8dp-7,   // c4
+    0x1.ca0d2931020eap-8,    // c5
+    -0x1.2cfcacfb49727p-8,   // c6
+    0x1.a542670ff1b05p-9,    // c7
+    -0x1.34e6f29c10c68p-9,   // c8
+    0x1.e27f3dba93b93p-10,   // c9
+    -0x1.79a6778274f33p-10,  // c10
 };
 __constant__ double kInterp[2] = {-1.0 / 12, 7.0 / 12};  // fields.py:94-96
 __constant__ double kGrav = GRAV;
@@ -171,10 +171,8 @@ __constant__ double kGrav = GRAV;
 __device__ __forceinline__ double pow1p_gamma_m1(double e)
 {
     const double e2 = e * e;
-    double a = kPow1p[12];
-    double b = kPow1p[11];
-    a = fma(a, e2, kPow1p[10]);
-    b = fma(b, e2, kPow1p[9]);
+    double a = kPow1p[10];
+    double b = kPow1p[9];
     a = fma(a, e2, kPow1p[8]);
     b = fma(b, e2, kPow1p[7]);
     a = fma(a, e2, kPow1p[6]);
@@ -196,6 +194,12 @@ __device__ __forceinline__ double rcp_pos(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if PMW_RCP_ITERS == 0
+    // one cubic step: r (1 + e + e^2) = (1/x)(1 - e^3), e <= 2^-19.9 -> 2^-59.7 before the final rounding
+    // (<= 0.51 ulp); three dependent FMAs instead of four
+    const double e0 = fma(-x, r, 1.0);
+    return fma(r, fma(e0, e0, e0), r);
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
