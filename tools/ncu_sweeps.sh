@@ -9,4 +9,4 @@ ncu --set full --clock-control none --import-source on -k regex:sweep_ -s 8 -c 2
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv --print-source sass > gpurun_out/prof_${TAG}_sass.csv 2>/dev/null
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page details > gpurun_out/prof_${TAG}_details.txt 2>/dev/null
-tail -3 gpurun_out/ncu_${TAG}1.log gpurun_out/ncu_${TAG}2.log
+tail -n 3 gpurun_out/ncu_${TAG}1.log gpurun_out/ncu_${TAG}2.log
