@@ -76,7 +76,7 @@ struct pmw_ctx {
     bool xhalo_valid[3];  // x halo columns hold the periodic image of the interior
     bool xhalo6_valid[3];  // ... and so do the four further columns a fused x sweep reads (6-wide image)
     // fused sweeps (pmw_sweep.cuh): 1 = pmw_evolve runs one kernel per directional sweep
-    int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt;
+    int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt, dyn_items;
     double* hydro_blob;
     double* src_w;  // gravity-wave forcing field or nullptr
     unsigned char* jet_rows;  // injection: [nz] mask of the inflow rows, or nullptr (periodic x)
@@ -101,6 +101,8 @@ struct pmw_ctx {
     unsigned long long* nbr_flags[2];
     unsigned long long* flags;       // mine: [0] left neighbour's epoch, [1] right's, [2] watchdog
     unsigned int* edge_counters;     // last-arriver counter of the push CTAs
+    unsigned long long* xitem_counter;  // work counter of the x sweeps (never reset, see SweepArgs::item_base)
+    unsigned long long xitem_base;
     unsigned long long epoch;        // number of x stages run since pmw_connect_peers
     std::vector<void*> ipc_opened;
     // chunked sweeps: the three stages of a sweep only couple cells along the sweep direction, so
@@ -173,6 +175,8 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->stats_partial = c->stats_out = nullptr;
     c->flags = nullptr;
     c->edge_counters = nullptr;
+    c->xitem_counter = nullptr;
+    c->xitem_base = 0;
     // two bands per sweep measured best at 2048x1024 (tools/chunk_probe.py); small grids stay whole
     c->chunks = ((long long)params->nx * params->nz >= (1ll << 20)) ? 2 : 1;
     for (int k = 0; k < 4; ++k) { c->cstream[k] = nullptr; c->ev_join[k] = nullptr; }
@@ -198,6 +202,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->keep_tmp = 1;
     c->sweep_lz = 0;  // 0 = choose from the grid (pick_sweep_lz)
     c->sweep_xp = 2;
+    c->dyn_items = 1;  // x sweeps of a slab ring draw their items from a counter (0 never, 2 always)
     c->sweep_zt = 0;  // z sweeps: 0 = streaming kernel (72 us at 2048x1024), 1 = transposing x-style kernel (90 us)
     c->l2p[PMW_BUF_STATE] = 0;
     c->l2p[PMW_BUF_TMP] = 1;
@@ -223,6 +228,8 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
             cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->flags, 4 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(c->flags, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&c->xitem_counter, sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(c->xitem_counter, 0, sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&c->edge_counters, 2 * sizeof(unsigned int)) != cudaSuccess ||
             cudaMemset(c->edge_counters, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
             pmw_destroy(c);
@@ -262,6 +269,7 @@ extern "C" int pmw_destroy(pmw_ctx* c)
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->flags) cudaFree(c->flags);
     if (c->edge_counters) cudaFree(c->edge_counters);
+    if (c->xitem_counter) cudaFree(c->xitem_counter);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     delete c;
     return PMW_OK;
@@ -315,6 +323,9 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
     } else if (!strcmp(key, "sweep_xp")) {
         NEED(value == 2 || value == 3, "sweep_xp must be 2 or 3");
         c->sweep_xp = value;
+    } else if (!strcmp(key, "dyn_items")) {
+        NEED(value >= 0 && value <= 2, "dyn_items must be 0, 1 or 2");
+        c->dyn_items = value;
     } else {
         return fail(PMW_EINVAL, "pmw_set_tuning: unknown key '%s'", key);
     }
@@ -335,6 +346,7 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     else if (!strcmp(key, "sweep_lz")) *value = c->sweep_lz;
     else if (!strcmp(key, "sweep_xp")) *value = c->sweep_xp;
     else if (!strcmp(key, "sweep_zt")) *value = c->sweep_zt;
+    else if (!strcmp(key, "dyn_items")) *value = c->dyn_items;
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
 }
@@ -1116,17 +1128,24 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         // persistent: every warp walks its own list of (row, tile) items; as many CTAs of 4 warps as
         // are resident at once
         const long long nitems = (long long)c->p.nz * ntx;
+        // "dyn_items": 0 never, 1 slab ring, 2 always (not with the gravity-wave forcing: single slab only)
+        const bool dyn_items = !has_src && (c->peers ? (c->dyn_items != 0) : (c->dyn_items == 2));
         if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
-#define GO(PP, PM, WT) do { if (has_src) GO_S(PP, PM, WT, true); else GO_S(PP, PM, WT, false); } while (0)
-#define GO_S(PP, PM, WT, SRC)                                                                           \
+#define GO(PP, PM, WT)                                                   \
+    do {                                                                 \
+        if (has_src) GO_S(PP, PM, WT, true, false);                      \
+        else if (dyn_items) GO_S(PP, PM, WT, false, true);               \
+        else GO_S(PP, PM, WT, false, false);                             \
+    } while (0)
+#define GO_S(PP, PM, WT, SRC, DYN)                                                                           \
     do {                                                                                                \
         using T = XSweepTile<PP>;                                                                       \
         static unsigned long long attr_done = 0;                                                        \
         static int per_sm[64];                                                                          \
         if (!(attr_done >> c->p.device & 1ull)) {                                                       \
-            if ((rc = set_smem(sweep_x<PP, PM, WT, SRC>, T::smem_bytes())) != PMW_OK) return rc;        \
+            if ((rc = set_smem(sweep_x<PP, PM, WT, SRC, DYN>, T::smem_bytes())) != PMW_OK) return rc;        \
             int nb = 0;                                                                                 \
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_x<PP, PM, WT, SRC>, 32 * T::WARPS, \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_x<PP, PM, WT, SRC, DYN>, 32 * T::WARPS, \
                                                                  T::smem_bytes()));                     \
             per_sm[c->p.device & 63] = std::max(nb, 1);                                                 \
             attr_done |= 1ull << c->p.device;                                                           \
@@ -1135,7 +1154,10 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
                                                   (nitems + T::WARPS - 1) / T::WARPS);                  \
         const int npush = a.push_epoch ? std::min(ncta, 8) : 0;                                         \
         const dim3 grid(ncta);                                                                          \
-        launch_ex(sweep_x<PP, PM, WT, SRC>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a, \
+        a.item_counter = dyn_items ? c->xitem_counter : nullptr;                                        \
+        a.item_base = c->xitem_base;                                                                    \
+        if (dyn_items) c->xitem_base += (unsigned long long)nitems + 1ull * ncta * T::WARPS;            \
+        launch_ex(sweep_x<PP, PM, WT, SRC, DYN>, grid, dim3(32 * T::WARPS), T::smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a, \
                   ntx, npush);                                                                          \
     } while (0)
 #define GO_P(PM, WT) do { if (P == 2) GO(2, PM, WT); else GO(3, PM, WT); } while (0)

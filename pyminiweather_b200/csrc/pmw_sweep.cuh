@@ -62,6 +62,11 @@ struct SweepArgs {
                           // "gravity", source.py:43-50); single periodic slab only
     double cd1, cd2, cd3;  // dt_s / d    per stage (cell_update, pmw_common.cuh)
     double cg1, cg2, cg3;  // dt_s * grav per stage
+    // x sweep, dynamic item assignment (slab ring; nullptr = static walk): a counter that is never reset; this
+    // launch owns the values item_base .. item_base + nitems + warps - 1 (every warp draws once at the
+    // start and once per item it processes)
+    unsigned long long* item_counter;
+    unsigned long long item_base;
 };
 
 // Slab ring, fused x sweep: the first row of CTAs stores this slab's own six edge columns of S
@@ -161,10 +166,7 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_MINB
 #define PMW_XSWEEP_MINB 3
 #endif
-#ifndef PMW_XSWEEP_ITER
-#define PMW_XSWEEP_ITER 1  // 1: walk the item list incrementally (no integer division per item)
-#endif
-template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false>
+template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false, bool DYNAMIC = false>
 #ifdef PMW_XSWEEP_MAXNREG
 __global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
 #else
@@ -203,23 +205,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     if (a.push_epoch && blockIdx.x < npush) push_halo6_role(a, npush);
 
     const unsigned long long pol = l2_policy(1);
-#if PMW_XSWEEP_ITER == 1
-    // Items without a division per item: (tile column index, row) of the NEXT item advance by the
-    // constant stride nwarps = dq * nz + dr.
-    const int dq = nwarps / nz, dr = nwarps - dq * nz;
-    int nc = w / nz, nk = w - nc * nz;
-    auto make_item = [&](int cidx, int k) {
-        XItem it;
-        it.k = k;
-        it.tx = !a.edge_last ? cidx : ((cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1));
-        it.c0 = it.tx * T::LC;
-        return it;
-    };
     auto request = [&](const XItem& it, int buf) {  // lane 0: start the load of the item's state row
-#else
-    auto request = [&](int n, int buf) {  // lane 0: start the load of item n's state row
-        const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
-#endif
         if (a.wait_epoch && !(a.dbg & 2)) {
             if (it.c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
             if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
@@ -229,28 +215,42 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         // map column 0 is interior column -6 (array column -4)
         tma_load_3d(sS + buf * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
     };
-#if PMW_XSWEEP_ITER == 1
-    XItem nxt = make_item(nc, nk);
-    if (w < nitems && lane == 0) request(nxt, 0);
-#else
-    if (w < nitems && lane == 0) request(w, 0);
-#endif
     const int src_lane = (lane + 1) & 31;
     int buf = 0;
     unsigned phase = 0;  // bit b: parity of the next completion of bars[b]
+    // Item assignment.  Single slab: static grid-stride walk (warp w takes items w, w + nwarps, ...).
+    // Slab ring (DYNAMIC instantiations): after its first, static item a warp DRAWS the next item
+    // number from a global counter (lane 0; the draw for the item after next is in flight while an item
+    // is computed, and its raw result is only decoded one item later, so the L2 round trip never stalls
+    // the in-order instruction stream).  The CTAs that first push the slab's edge columns to the
+    // neighbours start their items several microseconds late; statically they would finish that much
+    // later than everybody else, dynamically they simply draw fewer items (N=2: 126.8 -> 121.4 us/step).
+    // Item order is preserved, so the edge tile columns still come last.  On a single slab the static
+    // walk is 1.5 us faster per sweep and stays (compile-time switch: no cost there).  The counter is 32 bits wide, never reset and compared
+    // modulo 2^32: draw number v of this launch is item nwarps + v.
+    constexpr bool dynamic = DYNAMIC;
+    unsigned int* const ctr = reinterpret_cast<unsigned int*>(a.item_counter);
+    const unsigned int base32 = (unsigned int)a.item_base;
+    auto draw = [&]() -> unsigned int { return (dynamic && lane == 0) ? atomicAdd(ctr, 1u) : 0u; };
+    auto decode = [&](unsigned int raw_l0) -> int {
+        const unsigned int v = __shfl_sync(0xffffffffu, raw_l0, 0) - base32 + (unsigned int)nwarps;
+        return (int)min(v, (unsigned int)nitems);
+    };
+    unsigned int raw1 = draw();
+    int n = min(w, nitems);
+    if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0);
 #pragma unroll 1
-    for (int n = w; n < nitems; n += nwarps) {
-#if PMW_XSWEEP_ITER == 1
-        const XItem it = nxt;
-        nk += dr;
-        nc += dq;
-        if (nk >= nz) { nk -= nz; ++nc; }
-        nxt = make_item(nc, nk);
-        if (n + nwarps < nitems && lane == 0) request(nxt, buf ^ 1);
-#else
+    while (n < nitems) {
         const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
-        if (n + nwarps < nitems && lane == 0) request(n + nwarps, buf ^ 1);
-#endif
+        int n_next;
+        if (dynamic) {
+            n_next = decode(raw1);
+            raw1 = draw();  // decoded one item from now
+        } else {
+            n_next = min(n + nwarps, nitems);
+        }
+        if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nz, ntx, T::LC, a.edge_last), buf ^ 1);
+        n = n_next;
         const IfaceBg bg = bg_x(a.hy, it.k + HS);
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
