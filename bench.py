@@ -23,6 +23,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+# stdout when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the
+# whole run and the result goes to a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
+
 METRIC = "cell-updates/sec (fp64, per RK3 step)"
 UNIT = "cell-updates/s"
 NX_SLAB, NZ = 2048, 1024  # BASELINE config 2 (per-GPU slab); --nx/--nz override it for the size studies
@@ -198,7 +211,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -401,7 +414,7 @@ def run_gpu(args, rank, local_rank, world):
                      "event_pair_frac": (bytes_per_launch / (launch_ms * 1e-3) / 1e9 / peak) if launch_ms > 0 else None},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
