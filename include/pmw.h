@@ -152,7 +152,10 @@ int pmw_discrete_step(pmw_ctx *ctx, int direction, int init_buf, int forcing_buf
  * Default on the TMA variant: ONE kernel per directional sweep (the three RK stages fused, the
  * two intermediate states on chip, 6-cell halo recomputed; bit-identical to running the stages
  * one by one) -- tuning key "fuse".  The reference's state_tmp (its stage-2 array) is then
- * written by the last sweep of the call only ("keep_tmp"). */
+ * written by the last sweep of the call only ("keep_tmp").  The gravity-wave forcing
+ * (pmw_set_source_w) is applied inside the sweeps of a single periodic slab; a context with
+ * inflow rows (pmw_set_inflow: x is not periodic) runs the reference's own sequence instead --
+ * halo-fill kernel, then fused stage kernel, per stage (pmw_discrete_step x 6 per step). */
 int pmw_evolve(pmw_ctx *ctx, int nsteps, double dt);
 /* One RK stage (rk_stage = 1,2,3) of the fused step on the context's rotating buffers, for
  * callers that interleave their own work between stages (slab halo exchange).  The caller
@@ -215,7 +218,8 @@ int pmw_peer_status(pmw_ctx *ctx, int *timed_out);
  * Fused sweeps: "fuse" (0|1, default 1: pmw_evolve launches one kernel per directional sweep), "keep_tmp"
  * (0|1, default 1: the last sweep of a pmw_evolve call also writes state_tmp), "sweep_zt" (z sweep
  * organisation: 0 streaming [default], 1 transposing), "sweep_lz" (rows per segment of the streaming z sweep;
- * 0 = chosen from the grid), "sweep_xp" (passes of 64 interfaces per x tile: 2). */
+ * 0 = chosen from the grid), "sweep_xp" (passes of 64 interfaces per x tile: 2), "dyn_items" (x sweeps draw their
+ * work items from a global counter: 0 never, 1 on a slab ring [default], 2 always). */
 int pmw_set_tuning(pmw_ctx *ctx, const char *key, int value);
 int pmw_get_tuning(pmw_ctx *ctx, const char *key, int *value);
 
