@@ -112,3 +112,76 @@ def test_oracle_interpolate_vs_convolve2d():  # tests/unit/test_interpolate.py:1
         assert np.allclose(convolve2d(state[v, :, 2:202], k4[:, None], mode="same")[2:-1, :], vz[v])
         assert np.allclose(convolve2d(state[v, 2:102, :], -k3[None, :], mode="same")[:, 2:-1], d3x[v])
         assert np.allclose(convolve2d(state[v, :, 2:202], -k3[:, None], mode="same")[2:-1, :], d3z[v])
+
+
+# ---- host logic of the injection configuration and of the device-side init (no GPU needed) -----------
+@pytest.mark.parametrize("nz,zlen", [(50, 1e4), (64, 1e4), (37, 7.5e3), (1024, 1e4)])
+def test_inflow_row_mask_is_the_reference_condition(nz, zlen):
+    """_dispatch.inflow_row_mask (what pmw_set_inflow receives) against the oracle's restatement of
+    bcs.py:43-48, which is pinned on the reference's fixtures."""
+    from pyminiweather_b200._dispatch import inflow_row_mask
+    p = make_params(32, nz, "injection", zlen=zlen)
+    mask = inflow_row_mask(p)
+    assert mask.dtype == np.uint8 and mask.shape == (nz,)
+    np.testing.assert_array_equal(np.nonzero(mask)[0] + 2, no.inflow_rows(nz, p["dz"], zlen))
+    assert 0 < mask.sum() < nz
+    # the band is centred on 3/4 of the domain height and zlen/8 tall
+    rows = np.nonzero(mask)[0]
+    assert abs((rows.mean() + 0.5) * p["dz"] - 0.75 * zlen) <= p["dz"]
+    assert abs(rows.size * p["dz"] - zlen / 8) <= 2 * p["dz"]
+
+
+def test_check_ic_accepts_the_five_configurations_only():
+    from pyminiweather_b200._dispatch import check_ic
+    for ic in ("thermal", "collision", "density-current", "gravity", "injection"):
+        check_ic(ic)
+    with pytest.raises(ValueError, match="unknown ic_type"):
+        check_ic("squall-line")
+
+
+@pytest.mark.parametrize("ic", ["thermal", "collision", "density-current", "gravity", "injection"])
+def test_device_spec_describes_the_host_catalogue(ic):
+    """ics.device_spec (the pmw_ic_spec pmw_init_state integrates) evaluated with the HOST sampler
+    reproduces cell_quantities at arbitrary points: same bubbles, wind and background."""
+    from pyminiweather_b200.ics.initial_conditions import background, cell_quantities, device_spec
+    xlen = 2e4
+    rng = np.random.default_rng(5)
+    x, z = rng.uniform(0, xlen, 500), rng.uniform(0, 1e4, 500)
+    r, u, w, t, hr, ht = cell_quantities(ic, x, z, xlen)
+    bubbles, wind, bv0 = device_spec(ic, xlen)
+    t2 = np.zeros_like(x)
+    for amp, x0, z0, xrad, zrad in bubbles:
+        t2 = t2 + sample_ellipse_cosine(x, z, amp, x0, z0, xrad, zrad)
+    assert np.array_equal(t, t2) and np.all(u == wind) and not r.any() and not w.any()
+    hr2, ht2 = (hydro_const_bvfreq(z, bv0) if bv0 is not None else hydro_const_theta(z))
+    assert np.array_equal(hr, hr2) and np.array_equal(np.broadcast_to(ht, x.shape), np.broadcast_to(ht2, x.shape))
+    assert len(bubbles) <= 4
+
+
+def test_mesh_axes_are_the_meshgrid_rows():
+    from pyminiweather_b200.slab import SlabMesh
+    p = make_params(48, 20)
+    m = MeshData(p)
+    xa, za = m.get_axes_int_ext()
+    x, z = m.get_mesh_int_ext()
+    assert np.array_equal(x[0], xa) and np.array_equal(z[:, 0], za)
+    # slabs: each rank's axis is its part of the global one (to rounding of the shifted origin)
+    world, nxl = 3, 16
+    for r in range(world):
+        sa, sz = SlabMesh(dict(p, nx=nxl), r, world).get_axes_int_ext()
+        np.testing.assert_allclose(sa, xa[r * nxl: (r + 1) * nxl + 4], rtol=0, atol=1e-9)
+        assert np.array_equal(sz, za)
+
+
+def test_ic_spec_struct_matches_the_header():
+    """ctypes mirror of pmw_ic_spec: field order and capacity as declared in include/pmw.h."""
+    import os
+    import re
+    from pyminiweather_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pmw.h")).read()
+    body = re.search(r"typedef struct pmw_ic_spec \{(.*?)\} pmw_ic_spec;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b(?:int|double)\s+([^;]+);", body)
+    flat = [n.split("[")[0].strip() for decl in names for n in decl.split(",")]
+    assert flat == [f[0] for f in _lib.PmwIcSpec._fields_]
+    assert int(re.search(r"#define PMW_IC_MAX_BUBBLES (\d+)", hdr).group(1)) == _lib.PMW_IC_MAX_BUBBLES
