@@ -6,18 +6,20 @@
 // so a tile that carries a 6-cell halo along that direction (2 cells per stage) can run all of
 // them without touching HBM in between: the state is read once and written once per sweep,
 // 64 B/cell instead of the 256 B/cell the stage-by-stage kernels move.  At that traffic the
-// sweep is no longer HBM-bound on B200 but bound by the FP64 pipe (~95 FP64 instructions per
-// cell-stage), so the kernels below are organised around instruction count and FP64 issue, not
-// around bytes.  The arithmetic per cell-stage is interface_flux + the same update expressions as
+// sweep is no longer HBM-bound on B200 but bound by the FP64 pipe (58 FP64 instructions per
+// interface + 8 per cell update) and, at the occupancy the register file allows, by its latency, so
+// the kernels below are organised around instruction count, independent FP64 chains and FP64
+// issue, not around bytes.  The arithmetic per cell-stage is interface_flux + the same update expressions as
 // the stage kernels (pmw_tma.cuh): results are bit-identical to the stage-by-stage path, halo
 // cells of the intermediate states are simply recomputed by the neighbouring tile.
 //
-// x sweep (sweep_x).  A CTA owns TR rows x L = 64P-10 cells; one TMA box load brings the state
-// tile with its 6-column halo (64P+4 columns).  Afterwards every WARP is autonomous: it owns one
-// row, runs stage 1 over 64P-2 cells into a shared-memory row T1, stage 2 over 64P-6 cells into
-// T2, stage 3 over its 64P-10 owned cells straight to HBM -- each stage with the pass structure
-// of stage_x_tma (two interfaces per lane, the third flux by a rotating shuffle), separated only
-// by __syncwarp.  Periodic x: the halo columns are the 6-wide image of the opposite edge, written
+// x sweep (sweep_x).  Persistent and warp-autonomous: a work item is one row x L = 64P-10 owned
+// cells; a warp brings the item's state row with its 6-column halo (64P+4 columns, all four
+// variables) into shared memory with one TMA box load (the next item's row is in flight
+// meanwhile), runs stage 1 over 64P-2 cells into a shared-memory row T1, stage 2 over 64P-6 cells
+// into T2, stage 3 over its 64P-10 owned cells straight to HBM -- each stage with the pass
+// structure of stage_x_tma (two interfaces per lane, the third flux by a rotating shuffle),
+// separated only by __syncwarp.  Warps never synchronise with each other.  Periodic x: the halo columns are the 6-wide image of the opposite edge, written
 // by whichever sweep produced the state (set_bc_x, bcs.py:35-39, folded into the producer).
 //
 // z sweep (sweep_z).  A warp owns a strip of 32 columns (one per lane) and streams upwards through
