@@ -786,6 +786,8 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
 
 #ifndef PMW_ZSWEEP_UNIVERSAL
 #define PMW_ZSWEEP_UNIVERSAL 0  // 1: one straight-line iteration body for fill, steady state, drain and walls (pmw_zuni.cuh)
+                                // 2: hybrid -- the specialised steady body where it applies, the universal body for every
+                                //    other block of four iterations (NOT yet run on a GPU)
 #endif
 }  // namespace pmw
 #include "pmw_zuni.cuh"
@@ -957,7 +959,24 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
     // steady iterations (all three stages active, every cell valid, no wall): js <= j <= je
     const int js = max(lo3 + 7, 7), je = min(hi1, nz - 2);
     int j = lo1;
+#if PMW_ZSWEEP_UNIVERSAL == 2
+    const ZUDevEnv<POW_MODE> uenv{a, min(i, nx - 1)};
+    const ZUDevStream ust{zs, zs.f0, zs.last_cell};
+    const ZUDevOut uout{pout0, ptmp0, a.L.vstride, a.L.pitch, nx, col_ok, img_r, img_l};
+    const ZUBounds ub{lo1, hi1, lo2, hi2, lo3, hi3, nz};
+#endif
     while (j <= hi3 + 6) {
+#if PMW_ZSWEEP_UNIVERSAL == 2
+        if (!(j >= js && j + 3 <= je)) {  // a block of four that is not all steady: universal iterations
+            // (windows are in canonical order -- tap t in slot t -- at every block boundary, for both bodies)
+            zu_iter<0, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j, ub, uout);
+            zu_iter<1, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j + 1, ub, uout);
+            zu_iter<2, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j + 2, ub, uout);
+            zu_iter<3, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j + 3, ub, uout);
+            j += 4;
+            continue;
+        }
+#endif
         if (j >= js && j + 3 <= je) {
             double* po = pout0 + (long long)(j - 7) * a.L.pitch;
             double* pt = ptmp0 + (long long)(j - 7) * a.L.pitch;

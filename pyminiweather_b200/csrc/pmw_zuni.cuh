@@ -40,8 +40,8 @@ struct ZUBounds {
 
 // Rebuild the cells beyond a wall in the window of one stage whose current interface is k (taps are the
 // cells k-2 .. k+1).  Same cases as ZStage::step.
-template <int R0, class Env>
-PMW_ZU_FN void zu_wall(const Env& env, ZUStage& s, int k, int nz)
+template <int R0, class Env, class St>
+PMW_ZU_FN void zu_wall(const Env& env, St& s, int k, int nz)
 {
     if (k == 0) {  // cells -2, -1 from interior cell 0 = tap 2
         const double h2 = env.hd(2), h0 = env.hd(0), h1 = env.hd(1);
@@ -67,8 +67,9 @@ PMW_ZU_FN void zu_wall(const Env& env, ZUStage& s, int k, int nz)
 }
 
 // One iteration at window rotation R: stage 1 at interface j, stage 2 at j-3, stage 3 at j-6.
-template <int R, bool WRITE_TMP, bool HAS_SRC, class Env, class Stream, class Out>
-PMW_ZU_FN void zu_iter(const Env& env, const Stream& zs, ZUStage& s1, ZUStage& s2, ZUStage& s3, int j,
+// (St: any type with W[4][4] and fprev[4] -- ZUStage here, ZStage<POW_MODE> in the hybrid loop of sweep_z.)
+template <int R, bool WRITE_TMP, bool HAS_SRC, class Env, class Stream, class Out, class St>
+PMW_ZU_FN void zu_iter(const Env& env, const Stream& zs, St& s1, St& s2, St& s3, int j,
                        const ZUBounds& b, const Out& out)
 {
     const int nz = b.nz;
