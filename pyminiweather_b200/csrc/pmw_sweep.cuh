@@ -6,7 +6,7 @@
 // so a tile that carries a 6-cell halo along that direction (2 cells per stage) can run all of
 // them without touching HBM in between: the state is read once and written once per sweep,
 // 64 B/cell instead of the 256 B/cell the stage-by-stage kernels move.  At that traffic the
-// sweep is no longer HBM-bound on B200 but bound by the FP64 pipe (58 FP64 instructions per
+// sweep is no longer HBM-bound on B200 but bound by the FP64 pipe (57 FP64 instructions per
 // interface + 8 per cell update) and, at the occupancy the register file allows, by its latency, so
 // the kernels below are organised around instruction count, independent FP64 chains and FP64
 // issue, not around bytes.  The arithmetic per cell-stage is interface_flux + the same update expressions as
