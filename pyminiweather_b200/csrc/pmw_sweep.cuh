@@ -168,6 +168,9 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_MINB
 #define PMW_XSWEEP_MINB 3
 #endif
+#ifndef PMW_XSWEEP_BGPF
+#define PMW_XSWEEP_BGPF 0  // 1: load the hydrostatic profiles of the next item one item ahead (opt-in, not yet measured)
+#endif
 template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false, bool DYNAMIC = false>
 #ifdef PMW_XSWEEP_MAXNREG
 __global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
@@ -241,6 +244,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     unsigned int raw1 = draw();
     int n = min(w, nitems);
     if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0);
+#if PMW_XSWEEP_BGPF == 1
+    IfaceBg bg_pf = bg_x(a.hy, xsweep_item(min(n, nitems - 1), nz, ntx, T::LC, a.edge_last).k + HS);
+#endif
 #pragma unroll 1
     while (n < nitems) {
         const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
@@ -253,7 +259,13 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         }
         if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nz, ntx, T::LC, a.edge_last), buf ^ 1);
         n = n_next;
+#if PMW_XSWEEP_BGPF == 1
+        // hydrostatic profiles of the row: requested one item ahead, together with its state row
+        const IfaceBg bg = bg_pf;
+        bg_pf = bg_x(a.hy, xsweep_item(min(n_next, nitems - 1), nz, ntx, T::LC, a.edge_last).k + HS);
+#else
         const IfaceBg bg = bg_x(a.hy, it.k + HS);
+#endif
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
         const int rem = min(nx - it.c0, T::LC);
