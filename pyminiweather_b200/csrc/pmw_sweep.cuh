@@ -117,7 +117,16 @@ struct XSweepTile {
 #endif
     static constexpr int WARPS = PMW_XSWEEP_WARPS;  // per CTA (no block-level synchronisation: any number works)
     static constexpr int S_ELEMS = NVAR * FW;
+#ifndef PMW_XSWEEP_ROT3
+#define PMW_XSWEEP_ROT3 0  // 1: three row buffers with rotating roles instead of four (opt-in, NOT yet run on a GPU):
+                           //    12.7 KB per warp, so that 16 warps fit an SM when the kernel is built for 128 registers
+                           //    (-DPMW_XSWEEP_MINB=4); the next item's state row then loads during stage 3 only
+#endif
+#if PMW_XSWEEP_ROT3 == 1
+    static constexpr int WARP_ELEMS = 3 * S_ELEMS;  // three buffers: S, T1, T2 of the current item, roles rotate per item
+#else
     static constexpr int WARP_ELEMS = 4 * S_ELEMS;  // S[2] (double-buffered state row), T1, T2
+#endif
     static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16); }
 };
 
@@ -184,7 +193,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* const sS = reinterpret_cast<double*>(smem_raw) + warp * T::WARP_ELEMS;
+#if PMW_XSWEEP_ROT3 == 0
     double* const sT = sS + 2 * T::S_ELEMS;  // T1, then T2
+#endif
     uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS) + 2 * warp;
     static_assert((T::S_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
 
@@ -200,17 +211,24 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     }
     // columns of T1 / T2 no stage writes (zero: they only feed interfaces whose results are discarded):
     // T1 0, 1 and 64P .. 64P+3; T2 0 .. 3 and 64P-2 .. 64P+3
+#if PMW_XSWEEP_ROT3 == 1
+    // every buffer serves as S, T1 and T2 in turn: the columns no stage writes then hold finite values of
+    // an earlier role; only the very first use needs them defined
+    for (int e = lane; e < T::WARP_ELEMS; e += 32) sS[e] = 0.0;
+#else
     for (int e = lane; e < NVAR * 16; e += 32) {
         const int v = e >> 4, j = e & 15;
         if (j < 6) sT[v * FW + (j < 2 ? j : 64 * P - 2 + j)] = 0.0;
         else sT[T::S_ELEMS + v * FW + (j < 10 ? j - 6 : 64 * P - 12 + j)] = 0.0;
     }
+#endif
     __syncwarp();
     pdl_wait();  // everything below reads state produced by the previous kernel
     if (a.push_epoch && blockIdx.x < npush) push_halo6_role(a, npush);
 
     const unsigned long long pol = l2_policy(1);
-    auto request = [&](const XItem& it, int buf) {  // lane 0: start the load of the item's state row
+    // (ROT3: `slot` = row buffer the state row lands in, `buf` = barrier, alternating per item)
+    auto request = [&](const XItem& it, int buf, int slot = -1) {  // lane 0: start the load of the item's state row
         if (a.wait_epoch && !(a.dbg & 2)) {
             if (it.c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
             if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
@@ -218,8 +236,11 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old row before the TMA write
         mbar_arrive_expect_tx(bars + buf, (uint32_t)(T::S_ELEMS * sizeof(double)));
         // map column 0 is interior column -6 (array column -4)
-        tma_load_3d(sS + buf * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
+        tma_load_3d(sS + (PMW_XSWEEP_ROT3 == 1 ? slot : buf) * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
     };
+#if PMW_XSWEEP_ROT3 == 1
+    int s0 = 0;  // buffer that holds S of the current item; T1 = s0+1, T2 = s0+2 (mod 3)
+#endif
     const int src_lane = (lane + 1) & 31;
     int buf = 0;
     unsigned phase = 0;  // bit b: parity of the next completion of bars[b]
@@ -243,7 +264,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     };
     unsigned int raw1 = draw();
     int n = min(w, nitems);
-    if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0);
+    if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0, 0);
 #if PMW_XSWEEP_BGPF == 1
     IfaceBg bg_pf = bg_x(a.hy, xsweep_item(min(n, nitems - 1), nz, ntx, T::LC, a.edge_last).k + HS);
 #endif
@@ -257,7 +278,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         } else {
             n_next = min(n + nwarps, nitems);
         }
+#if PMW_XSWEEP_ROT3 == 0
         if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nz, ntx, T::LC, a.edge_last), buf ^ 1);
+#endif
         n = n_next;
 #if PMW_XSWEEP_BGPF == 1
         // hydrostatic profiles of the row: requested one item ahead, together with its state row
@@ -269,8 +292,15 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
         const int rem = min(nx - it.c0, T::LC);
+#if PMW_XSWEEP_ROT3 == 1
+        const int s1 = (s0 == 2) ? 0 : s0 + 1, s2 = (s1 == 2) ? 0 : s1 + 1;
+        const double* const rowS = sS + s0 * T::S_ELEMS + 2 * lane;
+        double* const rowT1 = sS + s1 * T::S_ELEMS + 2 * lane;
+        double* const rowT2 = sS + s2 * T::S_ELEMS + 2 * lane;
+#else
         const double* const rowS = sS + buf * T::S_ELEMS + 2 * lane;
         double* const rowT = sT + 2 * lane;
+#endif
         double* const po = a.out + idx(a.L, 0, it.k + HS, it.c0 - SWEEP_HALO + HS + 2 * lane);
         const long long tmp_off = a.tmp - a.out;
         const int i0 = it.c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
@@ -300,7 +330,11 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 bool ok = t >= tlo && t < thi;
                 if (s == 2) ok = ok && i < nx;
                 // stage 1 -> T1, stage 2 -> T2 (column t), stage 3 -> HBM
+#if PMW_XSWEEP_ROT3 == 1
+                double* const dst = (s == 2) ? po + 64 * q + 2 : (s == 0 ? rowT1 : rowT2) + 64 * q + 2;
+#else
                 double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + s * T::S_ELEMS + 64 * q + 2;
+#endif
                 const long long dvs = (s == 2) ? a.L.vstride : (long long)FW;
                 // All four variables' updates as ONE straight-line block (eight independent FP64 chains, the
                 // four shuffles in flight together), then the stores; the rare extra stores (periodic images
@@ -352,13 +386,22 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 }
             }
             __syncwarp();
+#if PMW_XSWEEP_ROT3 == 1
+            src = (s == 0) ? rowT1 : rowT2;
+            // T1 is dead once stage 2 is through: the next item's state row loads into its buffer during stage 3
+            if (s == 1 && n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), buf ^ 1, s1);
+#else
             src = rowT + s * T::S_ELEMS;
+#endif
             dts = (s == 0) ? a.dt2 : a.dt3;
             cds = (s == 0) ? a.cd2 : a.cd3;
             tlo += 2;
             thi -= 2;
         }
         buf ^= 1;
+#if PMW_XSWEEP_ROT3 == 1
+        s0 = s1;  // the row that just arrived is the next item's S; its T1 / T2 are this item's T2 / S buffers
+#endif
     }
 }
 
