@@ -127,7 +127,13 @@ struct XSweepTile {
 #else
     static constexpr int WARP_ELEMS = 4 * S_ELEMS;  // S[2] (double-buffered state row), T1, T2
 #endif
-    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16); }
+#ifndef PMW_XSWEEP_LEAN
+#define PMW_XSWEEP_LEAN 0  // 1: lane 0's flux for the pass to its left travels through 32 bytes of shared memory instead of
+                           //    four registers in every lane (opt-in, for the 128-register build: 32 bytes of spill
+                           //    instead of 64; re-reading the row's profile values per pass did not reduce it further;
+                           //    NOT yet run on a GPU)
+#endif
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16 + 32 * PMW_XSWEEP_LEAN); }
 };
 
 // Both interface fluxes of a lane's pair with ONE warp-uniform fallback branch (see
@@ -198,6 +204,10 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
 #endif
     uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS) + 2 * warp;
     static_assert((T::S_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
+#if PMW_XSWEEP_LEAN == 1
+    double* const kbuf = reinterpret_cast<double*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS + 2 * T::WARPS) + 4 * warp;
+    if (lane < 4) kbuf[lane] = 0.0;
+#endif
 
     const int nx = a.L.nx, nz = a.L.nz;
     const int nitems = nz * ntx;
@@ -313,7 +323,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
 #pragma unroll 1
         for (int s = 0; s < 3; ++s) {
             const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
+#if PMW_XSWEEP_LEAN == 0
             double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
+#endif
 #pragma unroll
             for (int q = P - 1; q >= 0; --q) {
                 if (q >= nq) continue;
@@ -343,9 +355,14 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 double2 xv[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
+#if PMW_XSWEEP_LEAN == 1
+                    double fr = __shfl_sync(0xffffffffu, f0[v], src_lane);  // flux through the pair's right face
+                    if (lane == 31) fr = kbuf[v];  // ... which for the last lane is lane 0's first flux of the pass to the right
+#else
                     const double give = (lane == 0) ? keep[v] : f0[v];
                     const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
                     keep[v] = f0[v];
+#endif
                     double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
                     if (s != 0) {
                         const Pair in = lds2(rowS + v * FW + 64 * q + 2);
@@ -364,6 +381,14 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                                              cell_update<false, false>(f1[v], fr, ib, cds, 0.0, 0.0, dts, 0.0));
                     }
                 }
+#if PMW_XSWEEP_LEAN == 1
+                __syncwarp();  // the last lane has read the previous hand-over
+                if (lane == 0) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) kbuf[v] = f0[v];
+                }
+                __syncwarp();
+#endif
                 if (ok) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs) = xv[v];  // generic store: shared or global
