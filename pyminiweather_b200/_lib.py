@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libpmw.so")
 SOURCES = ["pmw_api.cu"]
-HEADERS = ["pmw_common.cuh", "pmw_direct.cuh", "pmw_tma.cuh", "pmw_sweep.cuh", "pmw_aux.cuh", "pmw_unfused.cuh", "pmw_init.cuh"]
+HEADERS = sorted(f for f in os.listdir(os.path.join(_PKG, "csrc")) if f.endswith(".cuh"))  # every header is a dependency
 
 PMW_BUF_STATE, PMW_BUF_TMP = 0, 1
 PMW_DIR_X, PMW_DIR_Z = 1, 2

@@ -17,6 +17,7 @@
 #include "pmw_direct.cuh"
 #include "pmw_tma.cuh"
 #include "pmw_sweep.cuh"
+#include "pmw_zpipe.cuh"
 #include "pmw_unfused.cuh"
 #include "pmw_init.cuh"
 
@@ -76,13 +77,14 @@ struct pmw_ctx {
     bool xhalo_valid[3];  // x halo columns hold the periodic image of the interior
     bool xhalo6_valid[3];  // ... and so do the four further columns a fused x sweep reads (6-wide image)
     // fused sweeps (pmw_sweep.cuh): 1 = pmw_evolve runs one kernel per directional sweep
-    int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt, dyn_items;
+    int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt, sweep_z3, dyn_items;
     double* hydro_blob;
     double* src_w;  // gravity-wave forcing field or nullptr
     unsigned char* jet_rows;  // injection: [nz] mask of the inflow rows, or nullptr (periodic x)
     double jet_u, jet_theta;
     Hydro hy;
     bool hydro_set;
+    bool hydro_consistent;  // pressure_int == C0 * dens_theta_int^gamma (else: pow_mode falls back to libdevice)
     cudaStream_t stream;
     int reverse;
     // tuning
@@ -203,11 +205,13 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->sweep_lz = 0;  // 0 = choose from the grid (pick_sweep_lz)
     c->sweep_xp = 2;
     c->dyn_items = 1;  // x sweeps of a slab ring draw their items from a counter (0 never, 2 always)
+    c->sweep_z3 = 0;  // z sweeps: 1 = stage-pipelined CTA of three warps (pmw_zpipe.cuh), 0 = one warp per strip (sweep_z)
     c->sweep_zt = 0;  // z sweeps: 0 = streaming kernel (72 us at 2048x1024), 1 = transposing x-style kernel (90 us)
     c->l2p[PMW_BUF_STATE] = 0;
     c->l2p[PMW_BUF_TMP] = 1;
     c->spare = 2;
     c->hydro_set = false;
+    c->hydro_consistent = true;
     c->stream = 0;
     c->reverse = 0;
     c->x_tr = 4;
@@ -222,7 +226,9 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->ev_used = 0;
     c->stats_blocks = 148 * 8;
     {
-        const size_t nhy = (size_t)4 * (params->nz + 4) + (size_t)4 * (params->nz + 1);
+        // 8 profile tables + the packed interface table Hydro::int_pack (32-byte aligned, hence the slack)
+        const size_t nhy = (size_t)4 * (params->nz + 4) + (size_t)4 * (params->nz + 1) + 4 +
+                           (size_t)4 * (params->nz + 1 + 2 * HY_PACK_PAD);
         if (cudaMalloc(&c->hydro_blob, nhy * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_partial, (size_t)2 * c->stats_blocks * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess ||
@@ -320,6 +326,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         c->sweep_lz = value;
     } else if (!strcmp(key, "sweep_zt")) {
         c->sweep_zt = value ? 1 : 0;
+    } else if (!strcmp(key, "sweep_z3")) {
+        c->sweep_z3 = value ? 1 : 0;
     } else if (!strcmp(key, "sweep_xp")) {
         NEED(value == 2 || value == 3, "sweep_xp must be 2 or 3");
         c->sweep_xp = value;
@@ -346,6 +354,7 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     else if (!strcmp(key, "sweep_lz")) *value = c->sweep_lz;
     else if (!strcmp(key, "sweep_xp")) *value = c->sweep_xp;
     else if (!strcmp(key, "sweep_zt")) *value = c->sweep_zt;
+    else if (!strcmp(key, "sweep_z3")) *value = c->sweep_z3;
     else if (!strcmp(key, "dyn_items")) *value = c->dyn_items;
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
@@ -361,8 +370,9 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
     BIND(c);
     NEED(dens_cell && dens_theta_cell && dens_int && dens_theta_int && pressure_int,
          "pmw_set_hydrostatic: null profile");
-    const int ncell = c->p.nz + 4, nint = c->p.nz + 1;
-    std::vector<double> h((size_t)4 * ncell + (size_t)4 * nint);
+    const int ncell = c->p.nz + 4, nint = c->p.nz + 1, npack = nint + 2 * HY_PACK_PAD;
+    const size_t pack_off = ((size_t)4 * ncell + (size_t)4 * nint + 3) / 4 * 4;  // 32-byte aligned (cudaMalloc base is)
+    std::vector<double> h(pack_off + (size_t)4 * npack);
     double* q = h.data();
     double* o_dc = q;            q += ncell;
     double* o_dtc = q;           q += ncell;
@@ -372,6 +382,7 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
     double* o_dti = q;           q += nint;
     double* o_pi = q;            q += nint;
     double* o_idti = q;
+    double* o_pack = h.data() + pack_off;
     for (int k = 0; k < ncell; ++k) {
         NEED(dens_cell[k] > 0 && dens_theta_cell[k] > 0, "pmw_set_hydrostatic: non-positive cell profile at %d", k);
         o_dc[k] = dens_cell[k];
@@ -379,12 +390,27 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
         o_idtc[k] = 1.0 / dens_theta_cell[k];
         o_pc[k] = C0 * std::pow(dens_theta_cell[k], GAMMA);
     }
+    // The background-relative pressure (PMW_POW_BACKGROUND) evaluates the z perturbation pressure as
+    // hy_pressure_int * ((1+e)^gamma - 1), which is the reference's C0*(rho*theta)^gamma - hy_pressure_int
+    // (interpolate.py:160-165) only if the caller's pressure profile IS C0 * hy_dens_theta_int^gamma.  Profiles
+    // from init() are (initial.py:84-105); anything else gets the reference's own formula.
+    double worst = 0.0;
     for (int k = 0; k < nint; ++k) {
         NEED(dens_int[k] > 0 && dens_theta_int[k] > 0, "pmw_set_hydrostatic: non-positive interface profile at %d", k);
         o_di[k] = dens_int[k];
         o_dti[k] = dens_theta_int[k];
         o_pi[k] = pressure_int[k];
         o_idti[k] = 1.0 / dens_theta_int[k];
+        const double want = C0 * std::pow(dens_theta_int[k], GAMMA);
+        worst = std::max(worst, std::fabs(pressure_int[k] - want) / want);
+    }
+    c->hydro_consistent = worst <= 1e-12;
+    for (int j = 0; j < npack; ++j) {  // entry j = interface j - HY_PACK_PAD, clamped to the domain
+        const int k = std::min(std::max(j - HY_PACK_PAD, 0), nint - 1);
+        o_pack[4 * j + 0] = o_di[k];
+        o_pack[4 * j + 1] = o_dti[k];
+        o_pack[4 * j + 2] = o_idti[k];
+        o_pack[4 * j + 3] = o_pi[k];
     }
     CU_TRY(cudaMemcpyAsync(c->hydro_blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -397,6 +423,7 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
     c->hy.dens_theta_int = d;           d += nint;
     c->hy.pressure_int = d;             d += nint;
     c->hy.inv_dens_theta_int = d;
+    c->hy.int_pack = c->hydro_blob + pack_off + (size_t)4 * HY_PACK_PAD;
     c->hydro_set = true;
     return PMW_OK;
 }
@@ -650,7 +677,7 @@ static int launch_x_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
     const dim3 grid((c->p.nx + T::TC - 1) / T::TC, ty1 - ty0 + (a.push_epoch ? 1 : 0));
     if (ty1 == ty0) return PMW_OK;
     const size_t smem = T::smem_bytes(has_init);
-    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
 #define GO(HI, PM)                                                                   \
     do {                                                                             \
         static unsigned long long attr_done = 0; /* one bit per device */             \
@@ -681,7 +708,7 @@ static int launch_x_tma_src(pmw_ctx* c, bool has_init, const CUtensorMap& tf, co
     const dim3 grid((c->p.nx + T::TC - 1) / T::TC, ty1 - ty0 + (a.push_epoch ? 1 : 0));
     if (ty1 == ty0) return PMW_OK;
     const size_t smem = T::smem_bytes(has_init);
-    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
 #define GO(HI, PM)                                                                             \
     do {                                                                                       \
         static unsigned long long attr_done = 0;                                               \
@@ -710,7 +737,7 @@ static int launch_z_tma_src(pmw_ctx* c, bool has_init, const CUtensorMap& tf, co
     if (tx1 == tx0) return PMW_OK;
     const dim3 grid(tx1 - tx0, (c->p.nz + T::TR - 1) / T::TR);
     const size_t smem = T::smem_bytes(has_init);
-    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
 #define GO(HI, PM)                                                                         \
     do {                                                                                   \
         static unsigned long long attr_done = 0;                                           \
@@ -740,7 +767,7 @@ static int launch_z_tma(pmw_ctx* c, bool has_init, const CUtensorMap& tf, const 
     if (tx1 == tx0) return PMW_OK;
     const dim3 grid(tx1 - tx0, (c->p.nz + T::TR - 1) / T::TR);
     const size_t smem = T::smem_bytes(has_init);
-    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
 #define GO(HI, PM)                                                                 \
     do {                                                                           \
         static unsigned long long attr_done = 0; /* one bit per device */           \
@@ -841,7 +868,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     if (c->p.variant == PMW_VARIANT_DIRECT || (c->p.nx & 1)) {  // the TMA kernels pair cells in x
         const dim3 block(64, 4);
         const dim3 grid((c->p.nx + 63) / 64, (c->p.nz + 3) / 4 + (direction == PMW_DIR_X ? push_rows : 0));
-        const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+        const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
         if (direction == PMW_DIR_X) {
             if (fast) stage_x_direct<1><<<grid, block, 0, c->stream>>>(a);
             else stage_x_direct<0><<<grid, block, 0, c->stream>>>(a);
@@ -1037,13 +1064,15 @@ static bool fuse_ok(const pmw_ctx* c)
 // Rows per z-sweep segment: a warp (32 columns x lz rows) is the unit of work and every SM holds
 // kZWarps of them; pick the segment count that fills whole waves with the least recomputation.
 static const int kZWarpsPerSM = PMW_ZSWEEP_MINB;
-static int pick_sweep_lz(const pmw_ctx* c)
+// `units_per_sm` resident work units (warps of sweep_z, CTAs of sweep_z3) per SM; a unit costs
+// `stages * lz + fill` interface evaluations.
+static int pick_sweep_lz(const pmw_ctx* c, int units_per_sm = kZWarpsPerSM, double stages = 3.0, double fill = 26.0)
 {
     if (c->sweep_lz) return std::min(c->sweep_lz, c->p.nz);
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
     const long long strips = (c->p.nx + ZS_COLS - 1) / ZS_COLS;
-    const long long slots = (long long)nsm * kZWarpsPerSM;
+    const long long slots = (long long)nsm * units_per_sm;
     double best = 1e300;
     int best_lz = c->p.nz;
     for (int nseg = 1; nseg <= c->p.nz / 8; ++nseg) {
@@ -1051,8 +1080,8 @@ static int pick_sweep_lz(const pmw_ctx* c)
         if ((c->p.nz + lz - 1) / lz != nseg) continue;
         const long long warps = strips * nseg;
         const long long waves = (warps + slots - 1) / slots;
-        // time ~ waves x (work of one warp, with the recomputed rows) x (how full the SMs are)
-        const double per_warp = 3.0 * lz + 12.0 + 14.0;  // interface evaluations + pipeline fill
+        // time ~ waves x (work of one unit, with the recomputed rows) x (how full the SMs are)
+        const double per_warp = stages * lz + fill;  // interface evaluations + pipeline fill
         const double occupancy = (double)warps / (waves * slots);
         const double t = waves * per_warp * (0.35 + 0.65 * std::max(occupancy, 0.5));
         if (t < best) { best = t; best_lz = lz; }
@@ -1090,7 +1119,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     a.dbg = c->peer_dbg;
     a.src_w = c->src_w;
     const bool has_src = c->src_w != nullptr;
-    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND;
+    const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
     const CUtensorMap* tm = nullptr;
     int rc;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1197,6 +1226,33 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         else      { if (write_tmp) GO(0, true); else GO(0, false); }
 #undef GO
         LAUNCHED(c, "sweep_zt");
+    } else if (c->sweep_z3) {
+        // stage-pipelined z sweep: CTA = 3 warps = the three stages of one strip segment
+        if ((rc = get_tmap(c, pS, Z3_COLS, 4, &tm, true)) != PMW_OK) return rc;
+#define GO_S(PM, WT, SRC)                                                                                  \
+    do {                                                                                                   \
+        static unsigned long long attr_done = 0;                                                           \
+        static int per_sm[64];                                                                             \
+        if (!(attr_done >> c->p.device & 1ull)) {                                                          \
+            if ((rc = set_smem(sweep_z3<PM, WT, SRC>, z3_smem_bytes())) != PMW_OK) return rc;              \
+            int nb = 0;                                                                                    \
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_z3<PM, WT, SRC>, 32 * Z3_WARPS, \
+                                                                 z3_smem_bytes()));                        \
+            per_sm[c->p.device & 63] = std::max(nb, 1);                                                    \
+            attr_done |= 1ull << c->p.device;                                                              \
+        }                                                                                                  \
+        a.lz = pick_sweep_lz(c, per_sm[c->p.device & 63], 1.0, 14.0);                                      \
+        const dim3 grid((c->p.nx + Z3_COLS - 1) / Z3_COLS, (c->p.nz + a.lz - 1) / a.lz);                   \
+        if (e0) CU_TRY(cudaEventRecord(e0, c->stream));                                                    \
+        launch_ex(sweep_z3<PM, WT, SRC>, grid, dim3(32 * Z3_WARPS), z3_smem_bytes(), c->stream,            \
+                  c->pdl && !c->timing, *tm, a);                                                           \
+    } while (0)
+#define GO(PM, WT) do { if (has_src) GO_S(PM, WT, true); else GO_S(PM, WT, false); } while (0)
+        if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
+        else      { if (write_tmp) GO(0, true); else GO(0, false); }
+#undef GO
+#undef GO_S
+        LAUNCHED(c, "sweep_z3");
     } else {
         a.lz = pick_sweep_lz(c);
         if ((rc = get_tmap(c, pS, ZS_COLS, 1, &tm, true)) != PMW_OK) return rc;

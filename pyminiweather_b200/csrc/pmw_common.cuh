@@ -55,7 +55,12 @@ struct Hydro {
     const double* inv_dens_theta_cell;  // [nz+4]  1/dens_theta_cell
     const double* pressure_cell;        // [nz+4]  C0*dens_theta_cell^gamma
     const double* inv_dens_theta_int;   // [nz+1]  1/dens_theta_int
+    // the four interface profiles interleaved, {dens, dens_theta, 1/dens_theta, pressure} per interface, for
+    // interfaces -HY_PACK_PAD .. nz+HY_PACK_PAD (clamped copies beyond the domain): int_pack[4*k + 0..3];
+    // 32-byte aligned entries, so that a z sweep can pull them into shared memory with bulk copies
+    const double* int_pack;
 };
+constexpr int HY_PACK_PAD = 8;
 
 struct StageArgs {
     Layout L;
@@ -424,6 +429,14 @@ struct Flux4 {
 };
 // Arguments and result by value: nothing of the caller's is address-taken, so its flux arrays stay
 // in registers on the hot path.
+#ifdef PMW_NO_SLOWPATH  // development probe: what the out-of-line call costs the hot path (NOT a valid build)
+template <bool DIR_Z, int POW_MODE>
+__device__ __forceinline__ Flux4 interface_flux_slow(Taps, IfaceBg, double, bool)
+{
+    __trap();
+    return Flux4{{0.0, 0.0, 0.0, 0.0}};
+}
+#else
 template <bool DIR_Z, int POW_MODE>
 __device__ __noinline__ Flux4 interface_flux_slow(Taps t, IfaceBg bg, double hv, bool wall)
 {
@@ -431,6 +444,7 @@ __device__ __noinline__ Flux4 interface_flux_slow(Taps t, IfaceBg bg, double hv,
     interface_flux<DIR_Z, POW_MODE>(t.s[0], t.s[1], t.s[2], t.s[3], bg, hv, wall, r.f);
     return r;
 }
+#endif
 
 // Wall halo value for set_bc_z folded into a z stage (bcs.py:92-148): `interior` is the
 // value of the nearest interior row in the same column, hd_* the hydrostatic densities.

@@ -117,27 +117,33 @@ struct XSweepTile {
 #endif
     static constexpr int WARPS = PMW_XSWEEP_WARPS;  // per CTA (no block-level synchronisation: any number works)
     static constexpr int S_ELEMS = NVAR * FW;
-#ifndef PMW_XSWEEP_ROT3
-#define PMW_XSWEEP_ROT3 0  // 1: three row buffers with rotating roles instead of four (opt-in, NOT yet run on a GPU):
-                           //    12.7 KB per warp, so that 16 warps fit an SM when the kernel is built for 128 registers
-                           //    (-DPMW_XSWEEP_MINB=4); the next item's state row then loads during stage 3 only
-#endif
-#if PMW_XSWEEP_ROT3 == 1
-    static constexpr int WARP_ELEMS = 3 * S_ELEMS;  // three buffers: S, T1, T2 of the current item, roles rotate per item
-#else
     static constexpr int WARP_ELEMS = 4 * S_ELEMS;  // S[2] (double-buffered state row), T1, T2
-#endif
-#ifndef PMW_XSWEEP_LEAN
-#define PMW_XSWEEP_LEAN 0  // 1: lane 0's flux for the pass to its left travels through 32 bytes of shared memory instead of
-                           //    four registers in every lane (opt-in, for the 128-register build: 32 bytes of spill
-                           //    instead of 64; re-reading the row's profile values per pass did not reduce it further;
-                           //    NOT yet run on a GPU)
-#endif
-    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16 + 32 * PMW_XSWEEP_LEAN); }
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16); }
 };
 
 // Both interface fluxes of a lane's pair with ONE warp-uniform fallback branch (see
 // interface_flux_fast).
+template <int POW_MODE>
+__device__ __forceinline__ void xpair_fix(bool bad0, bool bad1, const double (&t0)[4], const double (&t1)[4],
+                                          const double (&t2)[4], const double (&t3)[4], const double (&t4)[4],
+                                          const IfaceBg& bg, double hv, double (&f0)[4], double (&f1)[4])
+{
+    Taps T;
+    if (bad0) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { T.s[0][v] = t0[v]; T.s[1][v] = t1[v]; T.s[2][v] = t2[v]; T.s[3][v] = t3[v]; }
+        const Flux4 g = interface_flux_slow<false, POW_MODE>(T, bg, hv, false);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) f0[v] = g.f[v];
+    }
+    if (bad1) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { T.s[0][v] = t1[v]; T.s[1][v] = t2[v]; T.s[2][v] = t3[v]; T.s[3][v] = t4[v]; }
+        const Flux4 g = interface_flux_slow<false, POW_MODE>(T, bg, hv, false);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) f1[v] = g.f[v];
+    }
+}
 template <int POW_MODE>
 __device__ __forceinline__ void xpair_flux(const double (&t0)[4], const double (&t1)[4], const double (&t2)[4],
                                            const double (&t3)[4], const double (&t4)[4], const IfaceBg& bg, double hv,
@@ -147,21 +153,7 @@ __device__ __forceinline__ void xpair_flux(const double (&t0)[4], const double (
     const bool bad1 = interface_flux_fast<false, POW_MODE>(t1, t2, t3, t4, bg, hv, false, f1);
     if (__any_sync(0xffffffffu, bad0 || bad1)) {
         asm volatile("" ::: "memory");  // keep the argument copies of the cold path inside the branch
-        Taps T;
-        if (bad0) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) { T.s[0][v] = t0[v]; T.s[1][v] = t1[v]; T.s[2][v] = t2[v]; T.s[3][v] = t3[v]; }
-            const Flux4 g = interface_flux_slow<false, POW_MODE>(T, bg, hv, false);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) f0[v] = g.f[v];
-        }
-        if (bad1) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) { T.s[0][v] = t1[v]; T.s[1][v] = t2[v]; T.s[2][v] = t3[v]; T.s[3][v] = t4[v]; }
-            const Flux4 g = interface_flux_slow<false, POW_MODE>(T, bg, hv, false);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) f1[v] = g.f[v];
-        }
+        xpair_fix<POW_MODE>(bad0, bad1, t0, t1, t2, t3, t4, bg, hv, f0, f1);
     }
 }
 
@@ -183,8 +175,8 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_MINB
 #define PMW_XSWEEP_MINB 3
 #endif
-#ifndef PMW_XSWEEP_BGPF
-#define PMW_XSWEEP_BGPF 0  // 1: load the hydrostatic profiles of the next item one item ahead (opt-in, not yet measured)
+#ifndef PMW_XSWEEP_DUAL
+#define PMW_XSWEEP_DUAL 0  // 1: both passes of a stage evaluated together (four interface evaluations in flight per lane)
 #endif
 template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false, bool DYNAMIC = false>
 #ifdef PMW_XSWEEP_MAXNREG
@@ -199,15 +191,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* const sS = reinterpret_cast<double*>(smem_raw) + warp * T::WARP_ELEMS;
-#if PMW_XSWEEP_ROT3 == 0
     double* const sT = sS + 2 * T::S_ELEMS;  // T1, then T2
-#endif
     uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS) + 2 * warp;
     static_assert((T::S_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
-#if PMW_XSWEEP_LEAN == 1
-    double* const kbuf = reinterpret_cast<double*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS + 2 * T::WARPS) + 4 * warp;
-    if (lane < 4) kbuf[lane] = 0.0;
-#endif
 
     const int nx = a.L.nx, nz = a.L.nz;
     const int nitems = nz * ntx;
@@ -221,36 +207,26 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     }
     // columns of T1 / T2 no stage writes (zero: they only feed interfaces whose results are discarded):
     // T1 0, 1 and 64P .. 64P+3; T2 0 .. 3 and 64P-2 .. 64P+3
-#if PMW_XSWEEP_ROT3 == 1
-    // every buffer serves as S, T1 and T2 in turn: the columns no stage writes then hold finite values of
-    // an earlier role; only the very first use needs them defined
-    for (int e = lane; e < T::WARP_ELEMS; e += 32) sS[e] = 0.0;
-#else
     for (int e = lane; e < NVAR * 16; e += 32) {
         const int v = e >> 4, j = e & 15;
         if (j < 6) sT[v * FW + (j < 2 ? j : 64 * P - 2 + j)] = 0.0;
         else sT[T::S_ELEMS + v * FW + (j < 10 ? j - 6 : 64 * P - 12 + j)] = 0.0;
     }
-#endif
     __syncwarp();
     pdl_wait();  // everything below reads state produced by the previous kernel
     if (a.push_epoch && blockIdx.x < npush) push_halo6_role(a, npush);
 
     const unsigned long long pol = l2_policy(1);
-    // (ROT3: `slot` = row buffer the state row lands in, `buf` = barrier, alternating per item)
-    auto request = [&](const XItem& it, int buf, int slot = -1) {  // lane 0: start the load of the item's state row
-        if (a.wait_epoch && !(a.dbg & 2)) {
+    auto request = [&](const XItem& it, int buf) {  // lane 0: start the load of the item's state row
+        if (a.wait_epoch) {
             if (it.c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
             if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old row before the TMA write
         mbar_arrive_expect_tx(bars + buf, (uint32_t)(T::S_ELEMS * sizeof(double)));
         // map column 0 is interior column -6 (array column -4)
-        tma_load_3d(sS + (PMW_XSWEEP_ROT3 == 1 ? slot : buf) * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
+        tma_load_3d(sS + buf * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
     };
-#if PMW_XSWEEP_ROT3 == 1
-    int s0 = 0;  // buffer that holds S of the current item; T1 = s0+1, T2 = s0+2 (mod 3)
-#endif
     const int src_lane = (lane + 1) & 31;
     int buf = 0;
     unsigned phase = 0;  // bit b: parity of the next completion of bars[b]
@@ -274,10 +250,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     };
     unsigned int raw1 = draw();
     int n = min(w, nitems);
-    if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0, 0);
-#if PMW_XSWEEP_BGPF == 1
-    IfaceBg bg_pf = bg_x(a.hy, xsweep_item(min(n, nitems - 1), nz, ntx, T::LC, a.edge_last).k + HS);
-#endif
+    if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0);
 #pragma unroll 1
     while (n < nitems) {
         const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
@@ -288,29 +261,14 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         } else {
             n_next = min(n + nwarps, nitems);
         }
-#if PMW_XSWEEP_ROT3 == 0
         if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nz, ntx, T::LC, a.edge_last), buf ^ 1);
-#endif
         n = n_next;
-#if PMW_XSWEEP_BGPF == 1
-        // hydrostatic profiles of the row: requested one item ahead, together with its state row
-        const IfaceBg bg = bg_pf;
-        bg_pf = bg_x(a.hy, xsweep_item(min(n_next, nitems - 1), nz, ntx, T::LC, a.edge_last).k + HS);
-#else
         const IfaceBg bg = bg_x(a.hy, it.k + HS);
-#endif
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
         const int rem = min(nx - it.c0, T::LC);
-#if PMW_XSWEEP_ROT3 == 1
-        const int s1 = (s0 == 2) ? 0 : s0 + 1, s2 = (s1 == 2) ? 0 : s1 + 1;
-        const double* const rowS = sS + s0 * T::S_ELEMS + 2 * lane;
-        double* const rowT1 = sS + s1 * T::S_ELEMS + 2 * lane;
-        double* const rowT2 = sS + s2 * T::S_ELEMS + 2 * lane;
-#else
         const double* const rowS = sS + buf * T::S_ELEMS + 2 * lane;
         double* const rowT = sT + 2 * lane;
-#endif
         double* const po = a.out + idx(a.L, 0, it.k + HS, it.c0 - SWEEP_HALO + HS + 2 * lane);
         const long long tmp_off = a.tmp - a.out;
         const int i0 = it.c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
@@ -323,30 +281,25 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
 #pragma unroll 1
         for (int s = 0; s < 3; ++s) {
             const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
-#if PMW_XSWEEP_LEAN == 0
             double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
-#endif
-#pragma unroll
-            for (int q = P - 1; q >= 0; --q) {
-                if (q >= nq) continue;
-                double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
+            // the five taps of a lane's interface pair in pass q
+            auto load_taps = [&](int q, double (&t0)[4], double (&t1)[4], double (&t2)[4], double (&t3)[4], double (&t4)[4]) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const double* p = src + v * FW + 64 * q;
                     const Pair u01 = lds2(p), u23 = lds2(p + 2);
                     t0[v] = u01.a; t1[v] = u01.b; t2[v] = u23.a; t3[v] = u23.b; t4[v] = p[4];
                 }
-                xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
+            };
+            // the pair's two cells from the fluxes of pass q (t2, t3: the cells' forcing values)
+            auto finish_pass = [&](int q, const double (&t2)[4], const double (&t3)[4], const double (&f0)[4],
+                                   const double (&f1)[4]) {
                 const int t = 64 * q + 2 * lane + 2;  // tile column of the left cell of the pair
                 const int i = i0 + 64 * q;
                 bool ok = t >= tlo && t < thi;
                 if (s == 2) ok = ok && i < nx;
                 // stage 1 -> T1, stage 2 -> T2 (column t), stage 3 -> HBM
-#if PMW_XSWEEP_ROT3 == 1
-                double* const dst = (s == 2) ? po + 64 * q + 2 : (s == 0 ? rowT1 : rowT2) + 64 * q + 2;
-#else
                 double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + s * T::S_ELEMS + 64 * q + 2;
-#endif
                 const long long dvs = (s == 2) ? a.L.vstride : (long long)FW;
                 // All four variables' updates as ONE straight-line block (eight independent FP64 chains, the
                 // four shuffles in flight together), then the stores; the rare extra stores (periodic images
@@ -355,14 +308,9 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 double2 xv[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-#if PMW_XSWEEP_LEAN == 1
-                    double fr = __shfl_sync(0xffffffffu, f0[v], src_lane);  // flux through the pair's right face
-                    if (lane == 31) fr = kbuf[v];  // ... which for the last lane is lane 0's first flux of the pass to the right
-#else
                     const double give = (lane == 0) ? keep[v] : f0[v];
                     const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
                     keep[v] = f0[v];
-#endif
                     double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
                     if (s != 0) {
                         const Pair in = lds2(rowS + v * FW + 64 * q + 2);
@@ -381,14 +329,6 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                                              cell_update<false, false>(f1[v], fr, ib, cds, 0.0, 0.0, dts, 0.0));
                     }
                 }
-#if PMW_XSWEEP_LEAN == 1
-                __syncwarp();  // the last lane has read the previous hand-over
-                if (lane == 0) {
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) kbuf[v] = f0[v];
-                }
-                __syncwarp();
-#endif
                 if (ok) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs) = xv[v];  // generic store: shared or global
@@ -409,24 +349,45 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                             *reinterpret_cast<double2*>(dst + v * dvs + tmp_off) = make_double2(t2[v], t3[v]);
                     }
                 }
+            };
+            bool done = false;
+            if constexpr (PMW_XSWEEP_DUAL == 1 && P == 2) if (nq == 2) {
+                // both passes at once: four independent interface evaluations per lane and one fallback vote
+                double a0[4], a1[4], a2[4], a3[4], a4[4], b0[4], b1[4], b2[4], b3[4], b4[4];
+                double fa0[4], fa1[4], fb0[4], fb1[4];
+                load_taps(1, a0, a1, a2, a3, a4);
+                load_taps(0, b0, b1, b2, b3, b4);
+                const bool ba0 = interface_flux_fast<false, POW_MODE>(a0, a1, a2, a3, bg, a.hv_coeff, false, fa0);
+                const bool bb0 = interface_flux_fast<false, POW_MODE>(b0, b1, b2, b3, bg, a.hv_coeff, false, fb0);
+                const bool ba1 = interface_flux_fast<false, POW_MODE>(a1, a2, a3, a4, bg, a.hv_coeff, false, fa1);
+                const bool bb1 = interface_flux_fast<false, POW_MODE>(b1, b2, b3, b4, bg, a.hv_coeff, false, fb1);
+                if (__any_sync(0xffffffffu, ba0 || ba1 || bb0 || bb1)) {
+                    asm volatile("" ::: "memory");
+                    xpair_fix<POW_MODE>(ba0, ba1, a0, a1, a2, a3, a4, bg, a.hv_coeff, fa0, fa1);
+                    xpair_fix<POW_MODE>(bb0, bb1, b0, b1, b2, b3, b4, bg, a.hv_coeff, fb0, fb1);
+                }
+                finish_pass(1, a2, a3, fa0, fa1);
+                finish_pass(0, b2, b3, fb0, fb1);
+                done = true;
+            }
+            if (!done) {
+#pragma unroll
+                for (int q = P - 1; q >= 0; --q) {
+                    if (q >= nq) continue;
+                    double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
+                    load_taps(q, t0, t1, t2, t3, t4);
+                    xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
+                    finish_pass(q, t2, t3, f0, f1);
+                }
             }
             __syncwarp();
-#if PMW_XSWEEP_ROT3 == 1
-            src = (s == 0) ? rowT1 : rowT2;
-            // T1 is dead once stage 2 is through: the next item's state row loads into its buffer during stage 3
-            if (s == 1 && n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), buf ^ 1, s1);
-#else
             src = rowT + s * T::S_ELEMS;
-#endif
             dts = (s == 0) ? a.dt2 : a.dt3;
             cds = (s == 0) ? a.cd2 : a.cd3;
             tlo += 2;
             thi -= 2;
         }
         buf ^= 1;
-#if PMW_XSWEEP_ROT3 == 1
-        s0 = s1;  // the row that just arrived is the next item's S; its T1 / T2 are this item's T2 / S buffers
-#endif
     }
 }
 
