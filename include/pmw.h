@@ -233,6 +233,11 @@ long long pmw_launch_count(pmw_ctx *ctx);
  * in milliseconds and the number of launches timed.  Uses CUDA events on the context stream. */
 int pmw_stage_timing(pmw_ctx *ctx, int enable);
 int pmw_stage_timing_read(pmw_ctx *ctx, double *mean_ms, long long *count);
+/* Roofline denominator of the fused sweeps (bench.py): the FP64 issue rate this GPU sustains, measured
+ * with independent chains of dependent DFMAs (4 chains per thread, 16 warps per SM, every SM) on the
+ * context's device.  *warp_dfma_per_s = warp-level DFMA instructions per second, whole chip (x 64 = FLOP/s);
+ * *sm_clock_mhz = SM clock the rate was normalised with when reporting instructions per clock (may be NULL). */
+int pmw_fp64_peak(pmw_ctx *ctx, double *warp_dfma_per_s, double *sm_clock_mhz);
 
 #ifdef __cplusplus
 }

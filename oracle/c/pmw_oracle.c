@@ -272,3 +272,27 @@ void pmwo_stats(const pmwo_case *c, const double *s, double out[2])
 
 size_t pmwo_flux_len(int nx, int nz) { return (size_t)4 * (nz + 1) * (nx + 1); }
 size_t pmwo_tend_len(int nx, int nz) { return (size_t)4 * nz * nx; }
+
+/* Thread control for bench.py's CPU arms: launchers such as torchrun export OMP_NUM_THREADS=1, so the
+ * baseline sets its team size explicitly and reports what the runtime actually granted. */
+#ifdef _OPENMP
+#include <omp.h>
+int pmwo_set_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+int pmwo_team_size(void)
+{
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp master
+        n = omp_get_num_threads();
+    }
+    return n;
+}
+#else
+int pmwo_set_threads(int n) { (void)n; return 1; }
+int pmwo_team_size(void) { return 1; }
+#endif

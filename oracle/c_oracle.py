@@ -45,7 +45,17 @@ def lib():
         _lib.pmwo_set_bc_x.argtypes = [C.POINTER(_Case), _dp]
         _lib.pmwo_set_bc_z.argtypes = [C.POINTER(_Case), _dp]
         _lib.pmwo_stats.argtypes = [C.POINTER(_Case), _dp, _dp]
+        _lib.pmwo_set_threads.argtypes = [C.c_int]
+        _lib.pmwo_set_threads.restype = C.c_int
+        _lib.pmwo_team_size.restype = C.c_int
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """Set the OpenMP team size explicitly (launchers export OMP_NUM_THREADS=1) and return the size of the
+    team a parallel region really gets."""
+    lib().pmwo_set_threads(int(n))
+    return int(lib().pmwo_team_size())
 
 
 def _p(a: np.ndarray):

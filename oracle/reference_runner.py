@@ -1,7 +1,8 @@
-"""Drive the REAL reference (``/root/reference``, read-only) in-process.
-TEST INFRASTRUCTURE ONLY -- and only usable inside the build container: the GPU
-box has no ``/root/reference``, so nothing marked ``gpu``, nor ``smoke()``, nor
-``bench.py`` may call into this module.
+"""Drive the REAL reference in-process: ``/root/reference`` (read-only mount of the build
+container) or, where that does not exist (the GPU box), the verbatim copy ``oracle/_ref`` that
+``oracle/make_ref.py`` makes (git-ignored; travels with the gpurun snapshot).
+TEST / BASELINE INFRASTRUCTURE ONLY: the checker in ``tests/`` and the timed CPU baseline of
+``bench.py``; the product never imports it.
 
 Used for two things:
   * validating ``oracle.numpy_oracle`` / ``oracle/c`` against the reference's own
@@ -17,11 +18,18 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PMW_REFERENCE_ROOT", "/root/reference")
+_MOUNT = os.environ.get("PMW_REFERENCE_ROOT", "/root/reference")
+_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = _MOUNT if os.path.isdir(os.path.join(_MOUNT, "pyminiweather")) else _COPY
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyminiweather"))
+
+
+def kind() -> str:
+    """Where the reference comes from: 'mount' (/root/reference) or 'copy' (oracle/_ref)."""
+    return "mount" if REFERENCE_ROOT == _MOUNT else "copy"
 
 
 def _import_reference():

@@ -21,6 +21,9 @@ from .engine import HYDRO_NAMES, DeviceSolver
 
 _foreign: dict[int, tuple] = {}
 _MAX_FOREIGN = 4  # contexts kept alive for foreign fields objects
+# sweep order (Z,X / X,Z) of the next evolve() per foreign fields object: outlives the eviction or
+# re-creation of the object's context (step.py of the reference keeps it in a module global)
+_sweep_order: dict[int, bool] = {}
 
 SUPPORTED_ICS = ("thermal", "collision", "density-current", "gravity", "injection")
 
@@ -95,6 +98,7 @@ def foreign_solver(fields, params) -> DeviceSolver:
             ref = weakref.ref(fields, lambda _r, i=id(fields): _drop(i))
         except TypeError:  # object without weakref support: pin it (bounded cache below)
             ref = (lambda f=fields: f)
+        solver.reverse_direction = _sweep_order.get(id(fields), False)
         ent = (key, solver, ref)
         _foreign[id(fields)] = ent
         while len(_foreign) > _MAX_FOREIGN:
@@ -108,10 +112,19 @@ def foreign_solver(fields, params) -> DeviceSolver:
     return solver
 
 
+def remember_sweep_order(fields, solver):
+    """Record the context's direction flag under the foreign object (see _sweep_order)."""
+    if len(_sweep_order) > 64:
+        _sweep_order.clear()
+    _sweep_order[id(fields)] = bool(solver.reverse_direction)
+
+
 def _drop(i):
     ent = _foreign.pop(i, None)
     if ent is not None:
         ent[1].close()
+        if ent[2]() is None:  # the fields object is gone: forget its sweep order
+            _sweep_order.pop(i, None)
 
 
 def writable_f64(arr, shape, name):

@@ -93,6 +93,7 @@ SIGNATURES = {
     "pmw_launch_count": (C.c_longlong, [_vp]),
     "pmw_stage_timing": (C.c_int, [_vp, C.c_int]),
     "pmw_stage_timing_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "pmw_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

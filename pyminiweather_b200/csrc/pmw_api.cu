@@ -288,11 +288,26 @@ extern "C" int pmw_set_stream(pmw_ctx* c, void* s)
     return PMW_OK;
 }
 
+// Slab ring: a wait on a neighbour's epoch flag is bounded (~2 s, wait_epoch in pmw_tma.cuh) so that a lost
+// peer cannot hang the GPU; the kernel then carries on with stale halo columns and raises flags[2].  Every
+// synchronising entry point turns that into an error -- results computed after a time-out are invalid.
+static int check_watchdog(pmw_ctx* c)
+{
+    if (!c->peers) return PMW_OK;
+    unsigned long long f = 0;
+    CU_TRY(cudaMemcpyAsync(&f, c->flags + 2, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (f != 0)
+        return fail(PMW_ECUDA, "slab ring: a neighbour's halo columns did not arrive within the watchdog time; "
+                               "the state of this context is invalid");
+    return PMW_OK;
+}
+
 extern "C" int pmw_synchronize(pmw_ctx* c)
 {
     BIND(c);
     CU_TRY(cudaStreamSynchronize(c->stream));
-    return PMW_OK;
+    return check_watchdog(c);
 }
 
 extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
@@ -311,7 +326,11 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
     } else if (!strcmp(key, "pdl")) {
         c->pdl = value ? 1 : 0;
     } else if (!strcmp(key, "peer_dbg")) {
+#ifdef PMW_DEV
         c->peer_dbg = value;
+#else
+        return fail(PMW_EINVAL, "pmw_set_tuning: 'peer_dbg' exists in development builds only (-DPMW_DEV)");
+#endif
     } else if (!strcmp(key, "l2_hints")) {
         c->l2_hints = value;
     } else if (!strcmp(key, "chunks")) {
@@ -497,7 +516,11 @@ extern "C" int pmw_upload_state(pmw_ctx* c, int buf, const double* host)
 {
     return copy_state(c, buf, const_cast<double*>(host), true, true);
 }
-extern "C" int pmw_download_state(pmw_ctx* c, int buf, double* host) { return copy_state(c, buf, host, false, true); }
+extern "C" int pmw_download_state(pmw_ctx* c, int buf, double* host)
+{
+    const int rc = copy_state(c, buf, host, false, true);
+    return rc != PMW_OK ? rc : check_watchdog(c);
+}
 extern "C" int pmw_upload_state_async(pmw_ctx* c, int buf, const double* host)
 {
     return copy_state(c, buf, const_cast<double*>(host), true, false);
@@ -611,6 +634,13 @@ extern "C" int pmw_bc_z(pmw_ctx* c, int buf)
 // wide = false: the reference-shaped array [4][nz+4][nx+4] (map column 0 = array column 0);
 // wide = true : the same rows with the 6-wide x halo of the fused sweeps, [4][nz+4][nx+12]
 //               (map column 0 = array column -4 = interior column -6).
+static const int kTmapCap = 256;
+// tuning sweeps create many box shapes: start over while no pointer into the cache is live
+static void trim_tmaps(pmw_ctx* c)
+{
+    if (c->tmaps.size() + 8 > (size_t)kTmapCap) c->tmaps.clear();
+}
+
 static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** out, bool wide = false)
 {
     const int key_buf = pbuf + (wide ? 16 : 0);
@@ -619,8 +649,10 @@ static int get_tmap(pmw_ctx* c, int pbuf, int bw, int bh, const CUtensorMap** ou
             *out = &k.map;
             return PMW_OK;
         }
-    if (c->tmaps.capacity() < 256) c->tmaps.reserve(256);  // keep returned pointers stable
-    if (c->tmaps.size() >= 256) c->tmaps.clear();           // tuning sweeps: start over
+    // returned pointers stay valid until the next trim_tmaps(): the vector never reallocates (reserve) and is
+    // only emptied by trim_tmaps, which the launch helpers call BEFORE they fetch the maps of a launch
+    if (c->tmaps.capacity() < kTmapCap) c->tmaps.reserve(kTmapCap);
+    if (c->tmaps.size() >= (size_t)kTmapCap) return fail(PMW_EINVAL, "tensor map cache full");
     TmapKey k;
     k.buf = key_buf; k.bw = bw; k.bh = bh;
     const cuuint64_t gdim[3] = {(cuuint64_t)(c->p.nx + (wide ? 2 * SWEEP_HALO : 2 * HS)), (cuuint64_t)(c->p.nz + 4),
@@ -802,6 +834,7 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
 {
     NEED(c->hydro_set, "stage: hydrostatic profiles not set (pmw_set_hydrostatic)");
     NEED(p_out != p_forcing, "internal: stage output aliases the stencil input");
+    trim_tmaps(c);
     StageArgs a;
     a.L = c->L;
     a.forcing = c->base[p_forcing];
@@ -818,7 +851,6 @@ static int launch_stage(pmw_ctx* c, int direction, int p_init, int p_forcing, in
     a.push_counter = c->edge_counters;
     a.tile_x0 = a.tile_y0 = 0;
     if (c->cur_nchunks == 1) c->launch_stream = c->stream;
-    a.dbg = c->peer_dbg;
     {   // l2_hints = decimal "abcd": a = forcing when init==forcing (stage 1), b = forcing otherwise,
         // c = init, d = out; each 0 normal | 1 evict_first | 2 evict_last
         const int h = c->l2_hints;
@@ -1091,6 +1123,7 @@ static int pick_sweep_lz(const pmw_ctx* c, int units_per_sm = kZWarpsPerSM, doub
 
 static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool write_tmp, double dt)
 {
+    trim_tmaps(c);
     NEED(c->hydro_set, "sweep: hydrostatic profiles not set (pmw_set_hydrostatic)");
     SweepArgs a;
     a.L = c->L;
@@ -1116,7 +1149,6 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     a.nbr_state_left = a.nbr_state_right = nullptr;
     a.nbr_flags_left = a.nbr_flags_right = nullptr;
     a.push_counter = c->edge_counters;
-    a.dbg = c->peer_dbg;
     a.src_w = c->src_w;
     const bool has_src = c->src_w != nullptr;
     const bool fast = c->p.pow_mode == PMW_POW_BACKGROUND && c->hydro_consistent;
@@ -1320,7 +1352,9 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
         const int dirs[2] = {c->reverse ? PMW_DIR_X : PMW_DIR_Z, c->reverse ? PMW_DIR_Z : PMW_DIR_X};
         for (int d = 0; d < 2; ++d) {
             int rc = PMW_OK;
-            if (fused && (c->peer_dbg & (dirs[d] == PMW_DIR_X ? 16 : 8))) continue;  // development: time one direction
+#ifdef PMW_DEV  // development builds only (tools/build_variant.py): time one direction of the fused step
+            if (fused && (c->peer_dbg & (dirs[d] == PMW_DIR_X ? 16 : 8))) continue;
+#endif
             if (fused) {
                 // state_tmp (the reference's stage-2 array) is only materialised by the last sweep of the call
                 rc = evolve_sweep_fused(c, dirs[d], dt, c->keep_tmp && n == nsteps - 1 && d == 1);
@@ -1359,8 +1393,11 @@ extern "C" int pmw_stats_device(pmw_ctx* c, int buf, double* dev_out2)
     CHECK_BUF(buf);
     NEED(dev_out2, "pmw_stats_device: null output");
     NEED(c->hydro_set, "pmw_stats: hydrostatic profiles not set");
+    // rho cv T = kconst * p (pmw_aux.cuh: cell_energy)
+    static const double kconst = (CV / C0) * std::pow(C0 / P0, RD / CP);
     stats_partial_kernel<<<c->stats_blocks, 256, 0, c->stream>>>(c->base[c->l2p[buf]], c->L, c->hy.dens_cell,
-                                                                c->hy.dens_theta_cell, c->stats_partial);
+                                                                c->hy.dens_theta_cell, c->hy.inv_dens_theta_cell,
+                                                                c->hy.pressure_cell, kconst, c->stats_partial);
     LAUNCHED(c, "stats_partial_kernel");
     stats_final_kernel<<<1, 256, 0, c->stream>>>(c->stats_partial, c->stats_blocks, c->p.dx * c->p.dz, dev_out2);
     LAUNCHED(c, "stats_final_kernel");
@@ -1374,7 +1411,7 @@ extern "C" int pmw_stats(pmw_ctx* c, int buf, double out[2])
     if (rc != PMW_OK) return rc;
     CU_TRY(cudaMemcpyAsync(out, c->stats_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    return PMW_OK;
+    return check_watchdog(c);
 }
 
 extern "C" int pmw_solution_variables(pmw_ctx* c, int buf, double* host_out)
@@ -1536,6 +1573,39 @@ extern "C" int pmw_peer_status(pmw_ctx* c, int* timed_out)
     CU_TRY(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     *timed_out = f[2] != 0;
+    return PMW_OK;
+}
+
+extern "C" int pmw_fp64_peak(pmw_ctx* c, double* warp_dfma_per_s, double* sm_clock_mhz)
+{
+    BIND(c);
+    NEED(warp_dfma_per_s, "pmw_fp64_peak: null output");
+    int nsm = 148, khz = 0;
+    CU_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device));
+    CU_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->p.device));
+    constexpr int NCH = 4, WARPS = 16, ITERS = 2000;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    dfma_probe_kernel<NCH><<<nsm, 32 * WARPS, 0, c->stream>>>(c->stats_out, 50, 0.999, 1e-3);  // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(e0, c->stream);
+        dfma_probe_kernel<NCH><<<nsm, 32 * WARPS, 0, c->stream>>>(c->stats_out, ITERS, 0.999, 1e-3);
+        cudaEventRecord(e1, c->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            return fail(PMW_ECUDA, "pmw_fp64_peak: %s", cudaGetErrorString(e));
+        }
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *warp_dfma_per_s = (double)nsm * WARPS * ITERS * 8.0 * NCH / (best * 1e-3);
+    if (sm_clock_mhz) *sm_clock_mhz = khz * 1e-3;
     return PMW_OK;
 }
 

@@ -128,9 +128,6 @@ __global__ void unpack_halo_x_kernel(double* s, const Layout L, const double* __
 }
 
 // ---- compute_stats (stats.py:16-33) ----------------------------------------------------------
-#ifndef PMW_STATS_ONEPOW
-#define PMW_STATS_ONEPOW 0  // 1: one pow per cell for the temperature (opt-in until it has run on a GPU)
-#endif
 __device__ __forceinline__ double warp_sum(double x)
 {
 #pragma unroll
@@ -138,32 +135,63 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-// Pass 1: grid-stride over interior cells, pairwise-ish accumulation (per thread, then
-// warp-shuffle tree, then one partial per block).  partial[2*b] = sum rho, [2*b+1] = sum(ke+ie).
+// Energy density of one cell, stats.py:19-33: rho (u^2 + w^2) + rho cv T with T = theta (p/p0)^(R/cp) and
+// p = C0 (rho theta)^gamma.  Because 1 + gamma R/cp = gamma (R = cp - cv), rho cv T = K p with the constant
+// K = (cv/C0) (C0/p0)^(R/cp): the two pow() of the reference collapse into the pressure, which is evaluated
+// relative to the row's hydrostatic value exactly as in the flux kernels (pow1p_gamma_m1; pow() itself
+// beyond |e| > 1/8).  Agreement with the two-pow form: ~2e-16 per cell.
+__device__ __forceinline__ double cell_energy(double dens, double mu, double mw, double rt, double hd, double hdt,
+                                              double ihdt, double kp_row, double k_c0, double& rho_out)
+{
+    const double rho = dens + hd;
+    rho_out = rho;
+    const double e = rt * ihdt;
+    double ie;
+    if (fabs(e) <= 0.125) ie = fma(kp_row, pow1p_gamma_m1(e), kp_row);
+    else ie = k_c0 * pow(rt + hdt, GAMMA);
+    return fma(mu, mu, mw * mw) / rho + ie;  // no 1/2 on the kinetic term (stats.py:27)
+}
+
+// Pass 1: items = (row, chunk of 512 columns), grid-stride; 16-byte loads (interior column 0 sits on a
+// 128-byte line, pmw_common.cuh), row constants hoisted, per-thread sums, warp-shuffle tree, one partial per
+// block.  partial[2*b] = sum rho, [2*b+1] = sum(ke+ie).  HBM-bound: 32 B per cell.
 __global__ void __launch_bounds__(256) stats_partial_kernel(const double* __restrict__ s, const Layout L,
                                                             const double* __restrict__ hd,
                                                             const double* __restrict__ hdt,
+                                                            const double* __restrict__ ihdt,
+                                                            const double* __restrict__ pcell, const double kconst,
                                                             double* partial)
 {
-    const long long n = (long long)L.nx * L.nz;
+    constexpr int CHUNK = 512;  // columns per item: one double2 per thread
+    const int nchunks = (L.nx + CHUNK - 1) / CHUNK;
+    const int nitems = L.nz * nchunks;
+    const double k_c0 = kconst * C0;
+    const bool vec = (L.nx & 1) == 0;
     double mass = 0.0, energy = 0.0;
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n;
-         c += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(c / L.nx), i = (int)(c % L.nx);
-        const double rho = s[idx(L, DENS, k + HS, i + HS)] + hd[k + HS];
-        const double u = s[idx(L, UMOM, k + HS, i + HS)] / rho;
-        const double w = s[idx(L, WMOM, k + HS, i + HS)] / rho;
-        const double th = (s[idx(L, RHOT, k + HS, i + HS)] + hdt[k + HS]) / rho;
-#if PMW_STATS_ONEPOW == 1
-        // T = theta * (p/p0)^(R/cp) with p = C0 (rho theta)^gamma: (C0/p0)^(R/cp) * (rho theta)^(gamma R/cp),
-        // one pow instead of two (5e-16 relative to the two-pow form per cell, sums equal to 1e-16)
-        const double t = th * (pow(C0 / P0, RD / CP) * pow(rho * th, GAMMA * RD / CP));
-#else
-        const double p = C0 * pow(rho * th, GAMMA);
-        const double t = th / pow(P0 / p, RD / CP);
-#endif
-        mass += rho;
-        energy += rho * (u * u + w * w) + rho * CV * t;  // no 1/2 on the kinetic term (stats.py:27)
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int k = item / nchunks, i = (item - k * nchunks) * CHUNK + 2 * threadIdx.x;
+        if (i >= L.nx) continue;
+        const double h = __ldg(hd + k + HS), ht = __ldg(hdt + k + HS), iht = __ldg(ihdt + k + HS);
+        const double kp = kconst * __ldg(pcell + k + HS);
+        const double* p = s + idx(L, 0, k + HS, i + HS);
+        double r0, r1;
+        if (vec) {
+            const double2 d = *reinterpret_cast<const double2*>(p);
+            const double2 u = *reinterpret_cast<const double2*>(p + L.vstride);
+            const double2 w = *reinterpret_cast<const double2*>(p + 2 * L.vstride);
+            const double2 t = *reinterpret_cast<const double2*>(p + 3 * L.vstride);
+            energy += cell_energy(d.x, u.x, w.x, t.x, h, ht, iht, kp, k_c0, r0);
+            energy += cell_energy(d.y, u.y, w.y, t.y, h, ht, iht, kp, k_c0, r1);
+            mass += r0 + r1;
+        } else {
+            energy += cell_energy(p[0], p[L.vstride], p[2 * L.vstride], p[3 * L.vstride], h, ht, iht, kp, k_c0, r0);
+            mass += r0;
+            if (i + 1 < L.nx) {
+                energy += cell_energy(p[1], p[L.vstride + 1], p[2 * L.vstride + 1], p[3 * L.vstride + 1], h, ht, iht, kp,
+                                      k_c0, r1);
+                mass += r1;
+            }
+        }
     }
     __shared__ double sm[2][8];
     mass = warp_sum(mass);
@@ -218,6 +246,26 @@ __global__ void solution_variables_kernel(const double* __restrict__ s, const La
     out[n + c] = s[idx(L, UMOM, k + HS, i + HS)] / rho;
     out[2 * n + c] = s[idx(L, WMOM, k + HS, i + HS)] / rho;
     out[3 * n + c] = (s[idx(L, RHOT, k + HS, i + HS)] + hdt[k + HS]) / rho - hdt[k + HS] / hd[k + HS];
+}
+
+
+// FP64 issue-rate probe (pmw_fp64_peak): NCH independent chains of dependent DFMAs per thread.
+template <int NCH>
+__global__ void dfma_probe_kernel(double* out, int iters, double a, double b)
+{
+    double x[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) x[c] = threadIdx.x * 1e-3 + c;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) x[c] = fma(x[c], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s += x[c];
+    if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
 }
 
 }  // namespace pmw

@@ -11,9 +11,6 @@
 // 16 doubles (128 B) and vstride = pitch * (nz+4).
 #pragma once
 #include <cuda_runtime.h>
-#ifndef PMW_RCP_ITERS
-#define PMW_RCP_ITERS 2
-#endif
 #include <stdint.h>
 
 namespace pmw {
@@ -92,7 +89,6 @@ struct StageArgs {
     unsigned long long* nbr_flags_left;
     unsigned long long* nbr_flags_right;
     unsigned int* push_counter;
-    int dbg;  // development switches (pmw_set_tuning "peer_dbg"); 0 in production
     // L2 eviction priority per operand: 0 normal, 1 evict_first, 2 evict_last (createpolicy)
     int hint_forcing, hint_init, hint_out;
     // Chunked sweeps: this launch covers only the tile columns (z stages) / tile rows (x stages)
@@ -199,20 +195,10 @@ __device__ __forceinline__ double rcp_pos(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#if PMW_RCP_ITERS == 0
-    // one cubic step: r (1 + e + e^2) = (1/x)(1 - e^3), e <= 2^-19.9 -> 2^-59.7 before the final rounding
-    // (<= 0.51 ulp); three dependent FMAs instead of four
-    const double e0 = fma(-x, r, 1.0);
-    return fma(r, fma(e0, e0, e0), r);
-#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
-#if PMW_RCP_ITERS >= 3
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-#endif
     return r;
 }
 
@@ -234,10 +220,6 @@ struct IfaceBg {
 // written out: ptxas may otherwise contract mul+add pairs differently in different kernels
 // (PTX mul/add without a rounding modifier are contractible), and then the two kernel
 // variants -- or two tiles of one kernel -- would disagree in the last bit for the same cell.
-#ifndef PMW_FLUX_ALG
-#define PMW_FLUX_ALG 1
-#endif
-#if PMW_FLUX_ALG == 1
 // Algebraically reduced form (default).  With m = val[UMOM or WMOM] the interpolated momentum along the
 // sweep and X = val[RHOT] + (rho*theta)_hy the interpolated rho*theta, the reference's
 //     u = m / rho;  t = X / rho;  rho*u -> m;  rho*t -> X;  rho*u*t -> u*X;  rho*u*u -> m*u
@@ -320,105 +302,6 @@ __device__ __forceinline__ bool interface_flux_fast(const double (&s0)[4], const
 {
     return interface_flux_core<DIR_Z, POW_MODE, true>(s0, s1, s2, s3, bg, hv, wall, flux);
 }
-#else
-template <bool DIR_Z, int POW_MODE>
-__device__ __forceinline__ void interface_flux(const double (&s0)[4], const double (&s1)[4],
-                                               const double (&s2)[4], const double (&s3)[4],
-                                               const IfaceBg& bg, double hv, bool wall,
-                                               double (&flux)[4])
-{
-    const double c0 = kInterp[0], c1 = kInterp[1];
-    double val[4], d3[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        val[v] = fma(c0, s3[v], fma(c1, s2[v], fma(c1, s1[v], c0 * s0[v])));
-        d3[v] = fma(-3.0, s2[v], fma(3.0, s1[v], -s0[v])) + s3[v];
-    }
-    const double rho = val[DENS] + bg.dens;
-    const double r = rcp_pos(rho);
-    const double u = val[UMOM] * r;
-    double w = val[WMOM] * r;
-    const double t = (val[RHOT] + bg.dens_theta) * r;
-    const double rt = rho * t;
-    double p;  // x: full pressure; z: pressure perturbation p - hy_pressure_int
-    if (POW_MODE == 1) {
-        const double e = (rt - bg.dens_theta) * bg.inv_dens_theta;
-        if (fabs(e) <= 0.125) {
-            const double f = pow1p_gamma_m1(e);
-            p = DIR_Z ? bg.pressure * f : fma(bg.pressure, f, bg.pressure);
-        } else {
-            p = C0 * pow(rt, GAMMA);
-            if (DIR_Z) p -= bg.pressure;
-        }
-    } else {
-        p = C0 * pow(rt, GAMMA);
-        if (DIR_Z) p -= bg.pressure;
-    }
-    if (DIR_Z) {
-        if (wall) { w = 0.0; d3[DENS] = 0.0; }
-        const double rw = rho * w;
-        flux[DENS] = fma(-hv, d3[DENS], rw);
-        flux[UMOM] = fma(-hv, d3[UMOM], rw * u);
-        flux[WMOM] = fma(-hv, d3[WMOM], fma(rho, w * w, p));
-        flux[RHOT] = fma(-hv, d3[RHOT], rw * t);
-    } else {
-        const double ru = rho * u;
-        flux[DENS] = fma(-hv, d3[DENS], ru);
-        flux[UMOM] = fma(-hv, d3[UMOM], fma(rho, u * u, p));
-        flux[WMOM] = fma(-hv, d3[WMOM], ru * w);
-        flux[RHOT] = fma(-hv, d3[RHOT], ru * t);
-    }
-}
-
-// The same evaluation without the range branch of the background-relative pressure: always the
-// polynomial; returns true when |e| > 1/8 (or NaN), in which case `flux` must be recomputed with
-// interface_flux.  The fused sweeps evaluate several interfaces per iteration and test all their
-// flags with one warp vote instead of one divergent branch per interface.  Identical operations in
-// identical order: where it returns false the result has the same bits as interface_flux.
-template <bool DIR_Z, int POW_MODE>
-__device__ __forceinline__ bool interface_flux_fast(const double (&s0)[4], const double (&s1)[4],
-                                                    const double (&s2)[4], const double (&s3)[4],
-                                                    const IfaceBg& bg, double hv, bool wall,
-                                                    double (&flux)[4])
-{
-    if (POW_MODE != 1) {
-        interface_flux<DIR_Z, POW_MODE>(s0, s1, s2, s3, bg, hv, wall, flux);
-        return false;
-    }
-    const double c0 = kInterp[0], c1 = kInterp[1];
-    double val[4], d3[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        val[v] = fma(c0, s3[v], fma(c1, s2[v], fma(c1, s1[v], c0 * s0[v])));
-        d3[v] = fma(-3.0, s2[v], fma(3.0, s1[v], -s0[v])) + s3[v];
-    }
-    const double rho = val[DENS] + bg.dens;
-    const double r = rcp_pos(rho);
-    const double u = val[UMOM] * r;
-    double w = val[WMOM] * r;
-    const double t = (val[RHOT] + bg.dens_theta) * r;
-    const double rt = rho * t;
-    const double e = (rt - bg.dens_theta) * bg.inv_dens_theta;
-    const double f = pow1p_gamma_m1(e);
-    const double p = DIR_Z ? bg.pressure * f : fma(bg.pressure, f, bg.pressure);
-    if (DIR_Z) {
-        if (wall) { w = 0.0; d3[DENS] = 0.0; }
-        const double rw = rho * w;
-        flux[DENS] = fma(-hv, d3[DENS], rw);
-        flux[UMOM] = fma(-hv, d3[UMOM], rw * u);
-        flux[WMOM] = fma(-hv, d3[WMOM], fma(rho, w * w, p));
-        flux[RHOT] = fma(-hv, d3[RHOT], rw * t);
-    } else {
-        const double ru = rho * u;
-        flux[DENS] = fma(-hv, d3[DENS], ru);
-        flux[UMOM] = fma(-hv, d3[UMOM], fma(rho, u * u, p));
-        flux[WMOM] = fma(-hv, d3[WMOM], ru * w);
-        flux[RHOT] = fma(-hv, d3[RHOT], ru * t);
-    }
-    return !(fabs(e) <= 0.125);
-}
-
-#endif  // PMW_FLUX_ALG
 
 // Out-of-line fallback of the fused sweeps (rare: |e| > 1/8 somewhere in the warp).
 struct Taps {
@@ -429,14 +312,6 @@ struct Flux4 {
 };
 // Arguments and result by value: nothing of the caller's is address-taken, so its flux arrays stay
 // in registers on the hot path.
-#ifdef PMW_NO_SLOWPATH  // development probe: what the out-of-line call costs the hot path (NOT a valid build)
-template <bool DIR_Z, int POW_MODE>
-__device__ __forceinline__ Flux4 interface_flux_slow(Taps, IfaceBg, double, bool)
-{
-    __trap();
-    return Flux4{{0.0, 0.0, 0.0, 0.0}};
-}
-#else
 template <bool DIR_Z, int POW_MODE>
 __device__ __noinline__ Flux4 interface_flux_slow(Taps t, IfaceBg bg, double hv, bool wall)
 {
@@ -444,7 +319,6 @@ __device__ __noinline__ Flux4 interface_flux_slow(Taps t, IfaceBg bg, double hv,
     interface_flux<DIR_Z, POW_MODE>(t.s[0], t.s[1], t.s[2], t.s[3], bg, hv, wall, r.f);
     return r;
 }
-#endif
 
 // Wall halo value for set_bc_z folded into a z stage (bcs.py:92-148): `interior` is the
 // value of the nearest interior row in the same column, hd_* the hydrostatic densities.

@@ -59,7 +59,6 @@ struct SweepArgs {
     unsigned long long* nbr_flags_left;
     unsigned long long* nbr_flags_right;
     unsigned int* push_counter;
-    int dbg;
     const double* src_w;  // HAS_SRC instantiations: [nz][nx] extra rho*w tendency of every stage (ic_type
                           // "gravity", source.py:43-50); single periodic slab only
     double cd1, cd2, cd3;  // dt_s / d    per stage (cell_update, pmw_common.cuh)
@@ -825,97 +824,8 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
     }
 }
 
-#ifndef PMW_ZSWEEP_UNIVERSAL
-#define PMW_ZSWEEP_UNIVERSAL 0  // 1: one straight-line iteration body for fill, steady state, drain and walls (pmw_zuni.cuh)
-                                // 2: hybrid -- the specialised steady body where it applies, the universal body for every
-                                //    other block of four iterations (NOT yet run on a GPU)
-#endif
 }  // namespace pmw
-#include "pmw_zuni.cuh"
 namespace pmw {
-
-// Device policies of the universal z iteration (pmw_zuni.cuh).
-template <int POW_MODE>
-struct ZUDevEnv {
-    const SweepArgs& a;
-    int col;  // this lane's column, clamped to the domain
-    __device__ __forceinline__ double hd(int idx) const { return __ldg(a.hy.dens_cell + idx); }
-    __device__ __forceinline__ double wall_value(int v, double interior, double h_in, double h_halo) const
-    {
-        return pmw::wall_value(v, interior, h_in, h_halo);
-    }
-    __device__ __forceinline__ IfaceBg bg(int k) const { return bg_z(a.hy, k); }
-    __device__ __forceinline__ int clampi(int x, int lo, int hi) const { return min(max(x, lo), hi); }
-    __device__ __forceinline__ bool flux(const double (&t0)[4], const double (&t1)[4], const double (&t2)[4],
-                                         const double (&t3)[4], const IfaceBg& bg, bool wall, double (&f)[4]) const
-    {
-        return interface_flux_fast<true, POW_MODE>(t0, t1, t2, t3, bg, a.hv_coeff, wall, f);
-    }
-    __device__ __forceinline__ void flux_slow(const double (&t0)[4], const double (&t1)[4], const double (&t2)[4],
-                                              const double (&t3)[4], const IfaceBg& bg, bool wall, double (&f)[4]) const
-    {
-        Taps T;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) { T.s[0][v] = t0[v]; T.s[1][v] = t1[v]; T.s[2][v] = t2[v]; T.s[3][v] = t3[v]; }
-        const Flux4 g = interface_flux_slow<true, POW_MODE>(T, bg, a.hv_coeff, wall);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) f[v] = g.f[v];
-    }
-    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
-    __device__ __forceinline__ void cold_path_fence() const { asm volatile("" ::: "memory"); }
-    __device__ __forceinline__ void syncwarp() const { __syncwarp(); }
-    __device__ __forceinline__ double src(int m) const { return __ldg(a.src_w + (long long)m * a.L.nx + col); }
-    template <bool HAS_SRC>
-    __device__ __forceinline__ double update(int v, double f_lo, double f_hi, double init, int stage, double dens,
-                                             double g) const
-    {
-        const double dt = stage == 1 ? a.dt1 : (stage == 2 ? a.dt2 : a.dt3);
-        const double cd = stage == 1 ? a.cd1 : (stage == 2 ? a.cd2 : a.cd3);
-        const double cg = stage == 1 ? a.cg1 : (stage == 2 ? a.cg2 : a.cg3);
-        if (v == WMOM) return cell_update<true, HAS_SRC>(f_lo, f_hi, init, cd, cg, dens, dt, g);
-        return cell_update<false, false>(f_lo, f_hi, init, cd, cg, 0.0, dt, 0.0);
-    }
-};
-
-struct ZUDevStream {
-    const ZStream& zs;
-    int f0, last_cell;
-    __device__ __forceinline__ void request_ahead(int m) const { if (zs.lane == 0) zs.request(m + ZS_AHEAD); }
-    __device__ __forceinline__ void wait(int m) const { zs.wait(m); }
-    __device__ __forceinline__ void load(int m, double (&r)[4]) const
-    {
-        const double* p = zs.row(m);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) r[v] = p[v * ZS_COLS];
-    }
-};
-
-struct ZUDevOut {
-    double* pout0;  // this lane's column of cell row 0, variable 0
-    double* ptmp0;
-    long long vstride;
-    int pitch, nx;
-    bool col_ok, img_r, img_l;
-    __device__ __forceinline__ void store(int krow, const double (&c)[4]) const
-    {
-        if (col_ok) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                double* q = pout0 + v * vstride + (long long)krow * pitch;
-                *q = c[v];
-                if (img_r) q[nx] = c[v];
-                if (img_l) q[-nx] = c[v];
-            }
-        }
-    }
-    __device__ __forceinline__ void store_tmp(int krow, const double (&t)[4]) const
-    {
-        if (col_ok) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) ptmp0[v * vstride + (long long)krow * pitch] = t[v];
-        }
-    }
-};
 
 #ifndef PMW_ZSWEEP_MINB
 #define PMW_ZSWEEP_MINB 8  // resident warps (= CTAs) per SM the register allocation aims at: 8 -> 255 registers
@@ -975,23 +885,6 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
     double* const ptmp0 = a.tmp + idx(a.L, 0, HS, min(i, nx - 1) + HS);
     const bool img_r = a.periodic && i < SWEEP_HALO, img_l = a.periodic && i >= nx - SWEEP_HALO;
 
-#if PMW_ZSWEEP_UNIVERSAL == 1
-    {
-        ZUStage u1, u2, u3;
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) { u1.W[t][v] = s1.W[t][v]; u2.W[t][v] = 0.0; u3.W[t][v] = 0.0; }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) u1.fprev[v] = u2.fprev[v] = u3.fprev[v] = 0.0;
-        const ZUDevEnv<POW_MODE> env{a, min(i, nx - 1)};
-        const ZUDevStream st{zs, zs.f0, zs.last_cell};
-        const ZUDevOut out{pout0, ptmp0, a.L.vstride, a.L.pitch, nx, col_ok, img_r, img_l};
-        const ZUBounds b{lo1, hi1, lo2, hi2, lo3, hi3, nz};
-        zu_segment<WRITE_TMP, HAS_SRC>(env, st, u1, u2, u3, b, out);
-        return;
-    }
-#endif
     // gravity-wave forcing of cell row m in this lane's column (rows beyond the domain: the cell is discarded)
     auto zsrc = [&](int m) -> double {
         if (!HAS_SRC) return 0.0;
@@ -1000,24 +893,7 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
     // steady iterations (all three stages active, every cell valid, no wall): js <= j <= je
     const int js = max(lo3 + 7, 7), je = min(hi1, nz - 2);
     int j = lo1;
-#if PMW_ZSWEEP_UNIVERSAL == 2
-    const ZUDevEnv<POW_MODE> uenv{a, min(i, nx - 1)};
-    const ZUDevStream ust{zs, zs.f0, zs.last_cell};
-    const ZUDevOut uout{pout0, ptmp0, a.L.vstride, a.L.pitch, nx, col_ok, img_r, img_l};
-    const ZUBounds ub{lo1, hi1, lo2, hi2, lo3, hi3, nz};
-#endif
     while (j <= hi3 + 6) {
-#if PMW_ZSWEEP_UNIVERSAL == 2
-        if (!(j >= js && j + 3 <= je)) {  // a block of four that is not all steady: universal iterations
-            // (windows are in canonical order -- tap t in slot t -- at every block boundary, for both bodies)
-            zu_iter<0, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j, ub, uout);
-            zu_iter<1, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j + 1, ub, uout);
-            zu_iter<2, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j + 2, ub, uout);
-            zu_iter<3, WRITE_TMP, HAS_SRC>(uenv, ust, s1, s2, s3, j + 3, ub, uout);
-            j += 4;
-            continue;
-        }
-#endif
         if (j >= js && j + 3 <= je) {
             double* po = pout0 + (long long)(j - 7) * a.L.pitch;
             double* pt = ptmp0 + (long long)(j - 7) * a.L.pitch;

@@ -201,7 +201,7 @@ stage_x_tma(const __grid_constant__ CUtensorMap tm_forcing, const __grid_constan
     __syncthreads();
     pdl_wait();  // everything below reads or overwrites state produced by the previous stage
     if (threadIdx.x == 0) {
-        if (a.wait_epoch && !(a.dbg & 2)) {
+        if (a.wait_epoch) {
             if (tx == 0) wait_epoch(a.flags, 0, a.wait_epoch);
             if (tx == ntx - 1) wait_epoch(a.flags, 1, a.wait_epoch);
         }

@@ -40,7 +40,7 @@ constexpr int Z3_RS = Z3_COLS, Z3_VS = 4 * Z3_COLS, Z3_GROUP = 4 * Z3_ROW;
 __host__ __device__ constexpr int z3_slot(int s) { return (s >> 2) * Z3_GROUP + (s & 3) * Z3_RS; }  // doubles
 constexpr int Z3_WARPS = 3;
 #ifndef PMW_Z3_MINB
-#define PMW_Z3_MINB 5
+#define PMW_Z3_MINB 4
 #endif
 // shared memory: state ring | T1 | T2 | interface-profile ring [32][4] | one mbarrier per group of four state rows
 constexpr int Z3_OFF_T1 = Z3_SRING * Z3_ROW, Z3_OFF_T2 = Z3_OFF_T1 + Z3_TRING * Z3_ROW,
@@ -153,6 +153,7 @@ sweep_z3(const __grid_constant__ CUtensorMap tm_rows, const SweepArgs a)
         for (int m = f0; m < f0 + Z3_AHEAD; m += 4) request(m);
 
     uint32_t tok = 0;
+    volatile double wsave[16];  // cold path only (see the steady block)
     ZStage<POW_MODE> st;
 #pragma unroll
     for (int t = 0; t < 4; ++t)
@@ -195,13 +196,13 @@ sweep_z3(const __grid_constant__ CUtensorMap tm_rows, const SweepArgs a)
         double f[4], c[4], in[4];                                                                                  \
         const bool bad = st.template flux_fast<(R) + 1>(a, bg, f);                                                 \
         if (__any_sync(0xffffffffu, bad)) { /* |e| > 1/8 somewhere: this iteration and the rest of the block run    \
-                                               the generic path (pow), from a window in canonical order */        \
+                                               the generic path (pow).  The window travels there in canonical      \
+                                               order through local memory, so that the join constrains no         \
+                                               register of the hot path (through registers the rotation below      \
+                                               degenerated into 27 moves per iteration) */                         \
             asm volatile("" ::: "memory"); /* keep the copies below inside the cold branch */                     \
-            double Wc[4][4];                                                                                       \
             _Pragma("unroll") for (int t = 0; t < 4; ++t)                                                          \
-                _Pragma("unroll") for (int v = 0; v < 4; ++v) Wc[t][v] = st.W[((R) + 1 + t) & 3][v];               \
-            _Pragma("unroll") for (int t = 0; t < 4; ++t)                                                          \
-                _Pragma("unroll") for (int v = 0; v < 4; ++v) st.W[t][v] = Wc[t][v];                               \
+                _Pragma("unroll") for (int v = 0; v < 4; ++v) wsave[4 * t + v] = st.W[((R) + 1 + t) & 3][v];       \
             r0 = (R);                                                                                              \
             pulled = true;                                                                                         \
             goto generic;                                                                                          \
@@ -239,6 +240,12 @@ sweep_z3(const __grid_constant__ CUtensorMap tm_rows, const SweepArgs a)
         }
     generic:
         // generic iterations: pipeline fill / drain, segment ends, walls, and |e| > 1/8 (interface_flux: pow)
+        if (pulled) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) st.W[t][v] = wsave[4 * t + v];
+        }
 #pragma unroll 1
         for (int r = r0; r < 4; ++r) {
             const int it = it0 + r;

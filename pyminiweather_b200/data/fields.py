@@ -94,9 +94,12 @@ class Fields:
             raise ValueError("params do not match the grid these fields were allocated for")
         if self._solver is None or self._solver_key != key:
             self.sync_host()
+            reverse = False
             if self._solver is not None:
+                reverse = self._solver.reverse_direction  # the sweep order belongs to the simulation, not the context
                 self._solver.close()
             self._solver = DeviceSolver(key[0], key[1], key[3], key[4], key[5], hs=key[2])
+            self._solver.reverse_direction = reverse
             self._solver_key = key
             self._source_ic = None
             self._host_dirty = {PMW_BUF_STATE: True, PMW_BUF_TMP: True}

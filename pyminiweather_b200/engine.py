@@ -266,6 +266,13 @@ class DeviceSolver:
     def launch_count(self) -> int:
         return int(self._lib.pmw_launch_count(self._h))
 
+    def fp64_peak(self):
+        """(warp-level DFMA instructions per second the GPU sustains, SM clock in MHz): the measured FP64
+        roofline of the fused sweeps (``pmw_fp64_peak``)."""
+        r, clk = C.c_double(), C.c_double()
+        check(self._lib.pmw_fp64_peak(self._h, C.byref(r), C.byref(clk)))
+        return r.value, clk.value
+
     def stage_timing(self, enable: bool):
         check(self._lib.pmw_stage_timing(self._h, 1 if enable else 0))
 

@@ -106,6 +106,12 @@ class SlabRing:
         if self.world > 1:
             self.dist.barrier()
 
+    def check(self):
+        """Peer mode: raise if an x sweep ever gave up waiting for a neighbour's halo columns (the kernels
+        bound that wait so that a lost peer cannot hang the GPU; the state is invalid afterwards)."""
+        if self.mode == "peer":
+            self.solver.synchronize()  # pmw_synchronize reports the watchdog as an error
+
     # -- halo exchange ---------------------------------------------------------------------
     def exchange_halo_x(self, buf: int):
         s, dist = self.solver, self.dist
@@ -150,6 +156,7 @@ class SlabRing:
     def stats(self):
         """Global (mass, energy): local reduction kernels + all-reduce of 2 doubles."""
         self.solver.stats_device(PMW_BUF_STATE, self.stats_buf.data_ptr())
+        self.check()
         if self.world > 1:
             self.dist.all_reduce(self.stats_buf)
         out = self.stats_buf.cpu().numpy()

@@ -1,19 +1,47 @@
 """Time integration: ``evolve`` and ``discrete_step`` (mirror of
 pyminiweather/solve/step.py:21-143), running on the fused sm_100a stage kernels.
 
-``evolve`` issues the six RK stages of one step as six kernel launches on rotating device
-buffers (no halo-fill kernels, no interpolation/flux/tendency arrays).  The reference keeps
-the sweep order in a module global (step.py:18); here it lives in the device context, and
-this module exposes the same name as a read/write convenience for the *native* fields of
-the last call.
+``evolve`` runs one time step as two fused sweep kernels (or six stage kernels) on rotating device
+buffers (no halo-fill kernels, no interpolation/flux/tendency arrays).
+
+Sweep order.  The reference keeps it in the module global ``reverse_direction`` (step.py:18,103,143):
+one flag for the whole process, so two simulations stepped alternately swap each other's sweep order.
+Here the flag belongs to the device context of a fields object (``pmw_get/set_reverse_direction``): every
+simulation alternates Z,X / X,Z on its own, starting Z,X -- for a single simulation per process, the only
+way the reference's driver uses it, that is the same sequence.  The flag survives whatever happens to the
+context behind a fields object (re-creation after ``params["dt"]`` changed, eviction of a foreign object's
+context: ``_dispatch.py`` keeps it by object).  ``step.reverse_direction`` reads the flag of the last call;
+assigning it (the reference's ``step.reverse_direction = False`` reset idiom) sets the flag of the NEXT call.
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
-from .._dispatch import check_ic, direction_id, foreign_solver, is_native, writable_f64
+from .._dispatch import (check_ic, direction_id, foreign_solver, is_native, remember_sweep_order,
+                         writable_f64)
 from .._lib import PMW_BUF_STATE, PMW_BUF_TMP
 from ..ics.directions import Directions  # noqa: F401  (re-exported like the reference)
+
+_last_solver = None  # weakref to the context of the last evolve() call
+
+
+def __getattr__(name):  # PEP 562: ``step.reverse_direction`` when it has not been assigned
+    if name == "reverse_direction":
+        s = _last_solver() if _last_solver is not None else None
+        return bool(s.reverse_direction) if s is not None else False
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def _sweep_order(solver):
+    """Apply a pending ``step.reverse_direction = X`` assignment to the context of this call."""
+    global _last_solver
+    g = globals()
+    if "reverse_direction" in g:
+        solver.reverse_direction = bool(g.pop("reverse_direction"))
+    _last_solver = weakref.ref(solver)
+
 
 # Strict (foreign-fields) mode: also bring state_tmp back after evolve.  It is scratch in
 # the reference; leaving it on the device halves the PCIe traffic of the drop-in call.
@@ -66,10 +94,12 @@ def evolve(params, fields, mesh, dt: float = 1e-4) -> None:
     check_ic(params["ic_type"])
     if is_native(fields):
         solver = fields.device(params)
+        _sweep_order(solver)
         solver.evolve(1, dt)
         fields.device_wrote(PMW_BUF_STATE, PMW_BUF_TMP)
         return
     solver = foreign_solver(fields, params)
+    _sweep_order(solver)
     shape = (4, params["nz"] + 2 * params["hs"], params["nx"] + 2 * params["hs"])
     state = writable_f64(fields.state, shape, "fields.state")
     solver.upload(PMW_BUF_STATE, state)
@@ -78,6 +108,7 @@ def evolve(params, fields, mesh, dt: float = 1e-4) -> None:
         # they are caller data that the x stages read
         solver.upload(PMW_BUF_TMP, writable_f64(fields.state_tmp, shape, "fields.state_tmp"))
     solver.evolve(1, dt)
+    remember_sweep_order(fields, solver)
     solver.download(PMW_BUF_STATE, out=state)
     if SYNC_STATE_TMP:
         solver.download(PMW_BUF_TMP, out=writable_f64(fields.state_tmp, shape, "fields.state_tmp"))

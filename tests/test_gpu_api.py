@@ -373,3 +373,26 @@ def test_device_init_of_slabs_matches_the_whole_domain():
         assert np.array_equal(got, s.download(1))
         s.close()
     whole.close()
+
+
+def test_sweep_order_belongs_to_the_simulation_and_can_be_reset():
+    """step.py:18,103,143 of the reference: Z,X then X,Z alternating.  The flag survives the re-creation of a
+    fields object's context (dt changed) and the reference's reset idiom ``step.reverse_direction = False``
+    restarts the sequence."""
+    import pyminiweather_b200.solve.step as step
+    from pyminiweather_b200.solve import evolve
+    p, f, mesh = native_fields(64, 32, "thermal")
+    _, case = new_case(64, 32, "thermal")
+    evolve(p, f, mesh, dt=p["dt"]); no.evolve(case)
+    assert step.reverse_direction is True
+    p2 = dict(p, dt=p["dt"] / 2)            # new context behind the same fields: the order carries over
+    evolve(p2, f, mesh, dt=p2["dt"])
+    case.dt = p2["dt"]; no.evolve(case)
+    assert step.reverse_direction is False
+    assert worst_rel_l2(f.state, case.state) <= 1e-11
+    evolve(p2, f, mesh, dt=p2["dt"]); no.evolve(case)       # Z,X again -> flag True
+    step.reverse_direction = False                          # the reference's reset before a new run
+    evolve(p2, f, mesh, dt=p2["dt"])
+    case.reverse_direction = False; no.evolve(case)
+    assert worst_rel_l2(f.state, case.state) <= 1e-11
+    f.close()

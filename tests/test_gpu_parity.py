@@ -234,6 +234,53 @@ def test_pow_fallback_branch_large_perturbation():
         s.close()
 
 
+@pytest.mark.parametrize("zsweep", [dict(sweep_zt=1), dict(), dict(sweep_z3=1)], ids=["z-transposing", "z-streaming", "z-pipelined"])
+def test_fused_sweeps_pow_fallback_is_bitwise_the_staged_path(zsweep):
+    """|eps| > 1/8 inside the FUSED sweeps: a patch of the domain carries 20 % rho*theta perturbations, so
+    some warps leave the polynomial (cold call in the x and streaming z sweeps, bail-out to the generic
+    iteration in the pipelined z sweep) while their neighbours do not.  Same bits as the stage-by-stage
+    kernels, and the oracle's values; the diagnostics kernel takes its own pow() branch on this state."""
+    p, case = synthetic_case(300, 140, seed=5)
+    rng = np.random.default_rng(11)
+    patch = np.zeros((140, 300))
+    patch[30:75, 40:170] = rng.uniform(-1, 1, (45, 130))
+    case.state[3, 2:-2, 2:-2] += 0.2 * case.hy_dens_theta_cell[2:-2, None] * patch
+    case.state_tmp[:] = case.state
+    a, b = solver_for(case, fuse=0), solver_for(case, fuse=1, **dict(zsweep, sweep_lz=32))
+    m, e = b.stats(STATE)
+    mo, eo = no.compute_stats(case)
+    assert abs(m - mo) / mo <= STATS_TOL and abs(e - eo) / eo <= STATS_TOL
+    a.evolve(3); b.evolve(3)
+    ra, rb = a.download(STATE), b.download(STATE)
+    assert np.array_equal(ra[:, 2:-2, :], rb[:, 2:-2, :])
+    assert np.array_equal(interior(a.download(TMP)), interior(b.download(TMP)))
+    for _ in range(3):
+        no.evolve(case)
+    assert worst_rel_l2(rb, case.state) <= STATE_TOL
+    a.close(); b.close()
+
+
+def test_stats_odd_width_and_inconsistent_pressure_profile():
+    """compute_stats on an odd nx (scalar loads instead of 16-byte ones), and a caller-supplied
+    hy_pressure_int that is NOT C0*hy_dens_theta_int^gamma: the background-relative pressure would then
+    differ from the reference's formula (interpolate.py:160-165), so the context falls back to pow()."""
+    p, case = synthetic_case(101, 37, seed=2)
+    s = solver_for(case, "direct")
+    m, e = s.stats(STATE)
+    mo, eo = no.compute_stats(case)
+    assert abs(m - mo) / mo <= STATS_TOL and abs(e - eo) / eo <= STATS_TOL
+    s.close()
+    p, case = synthetic_case(96, 40, seed=4)
+    case.hy_pressure_int *= 1.0 + 1e-6 * np.arange(case.hy_pressure_int.size)
+    for fuse in (0, 1):
+        c = case.copy()
+        s = solver_for(c, fuse=fuse)
+        s.evolve(2)
+        no.evolve(c); no.evolve(c)
+        assert worst_rel_l2(s.download(STATE), c.state) <= STATE_TOL
+        s.close()
+
+
 # ---- mid-size grids -----------------------------------------------------------------------------
 def test_thermal_512x256_5_steps_vs_reference_subsample():
     g = golden("evolve_thermal_512x256_5steps_sub8.npz")
@@ -329,12 +376,13 @@ def test_chunked_sweeps_are_bitwise_identical(chunks):
     (236, 40, 2, dict(sweep_lz=8)),                # nx = 2 full x tiles exactly (rem == tile)
     (238, 40, 2, dict(sweep_lz=13)),               # ... plus a 2-cell remainder tile
 ])
-@pytest.mark.parametrize("zt", [1, 0])
-def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode, zt):
+@pytest.mark.parametrize("zsweep", [dict(sweep_zt=1), dict(), dict(sweep_z3=1)], ids=["z-transposing", "z-streaming", "z-pipelined"])
+def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode, zsweep):
     """One kernel per directional sweep (T1, T2 on chip, 6-cell halo recomputed) against one kernel
-    per RK stage: identical bits for the state (interior and x halo images) and for state_tmp."""
+    per RK stage: identical bits for the state (interior and x halo images) and for state_tmp -- for every
+    organisation of the z sweep (streaming warp, transposing CTA, three-warp stage pipeline)."""
     p, case = synthetic_case(nx, nz, seed=nx + nz)
-    a, b = solver_for(case, "tma", pow_mode, fuse=0), solver_for(case, "tma", pow_mode, fuse=1, sweep_zt=zt, **tune)
+    a, b = solver_for(case, "tma", pow_mode, fuse=0), solver_for(case, "tma", pow_mode, fuse=1, **dict(tune, **zsweep))
     for n in (1, steps):  # an odd and a longer call: both sweep orders, tmp written by the last sweep only
         a.evolve(n)
         b.evolve(n)

@@ -9,7 +9,7 @@ out = os.path.join(ROOT, "pyminiweather_b200", "variants", f"libpmw_{tag}.so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
 cmd = [_lib.nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17",
-       "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-o", out] + flags + [os.path.join(ROOT, "pyminiweather_b200", "csrc", "pmw_api.cu")]
+       "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-DPMW_DEV", "-o", out] + flags + [os.path.join(ROOT, "pyminiweather_b200", "csrc", "pmw_api.cu")]
 res = subprocess.run(cmd, env=env, capture_output=True, text=True)
 if res.returncode:
     print(res.stderr[-3000:]); sys.exit(1)

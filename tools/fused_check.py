@@ -1,5 +1,6 @@
 """Fused sweeps against the stage-by-stage path, bit for bit, on a list of grids; prints where they differ.
-usage: python tools/fused_check.py nx,nz[,lz] ...   (run on a GPU; PMW_LIB selects the library)"""
+usage: python tools/fused_check.py nx,nz[,lz] ... [key=value ...]   (run on a GPU; PMW_LIB selects the library;
+key=value pairs are tuning switches of the fused solver, e.g. sweep_z3=1)"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,10 +19,11 @@ def solver_for(case, variant="tma", pow_mode="background", **tuning):
 
 
 bad = 0
-for spec in sys.argv[1:]:
+extra = {k: int(v) for k, v in (a.split("=") for a in sys.argv[1:] if "=" in a)}
+for spec in [a for a in sys.argv[1:] if "=" not in a]:
     v = [int(x) for x in spec.split(",")]
     nx, nz = v[:2]
-    tune = dict(sweep_lz=v[2]) if len(v) > 2 else {}
+    tune = dict(extra, sweep_lz=v[2]) if len(v) > 2 else dict(extra)
     p, case = synthetic_case(nx, nz, seed=nx + nz)
     a, b = solver_for(case, "tma", "background", fuse=0), solver_for(case, "tma", "background", fuse=1, **tune)
     for n in (1, 4):

@@ -1,6 +1,8 @@
 """Coefficients of the pressure polynomial (csrc/pmw_common.cuh: kPow1p): f(e) = (1+e)^gamma - 1 = e * g(e),
 g interpolated at Chebyshev nodes on [-R, R] by a polynomial of degree N (so f has degree N+1).
-usage: python tools/pow_poly.py [N [R]]   -- prints the double coefficients and the error vs mpmath."""
+usage: python tools/pow_poly.py [N [R [EXPONENT]]]   -- prints the double coefficients and the error vs mpmath.
+EXPONENT defaults to gamma; "stats" selects 1 + gamma*R_d/c_p, the exponent of rho*theta in the internal
+energy of compute_stats (csrc/pmw_aux.cuh: kPowStats)."""
 import sys
 import mpmath as mp
 import numpy as np
@@ -8,6 +10,8 @@ mp.mp.dps = 60
 GAMMA = mp.mpf("1.40027894002789400278940027894")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 11
 R = mp.mpf(sys.argv[2]) if len(sys.argv) > 2 else mp.mpf(1) / 8
+if len(sys.argv) > 3:
+    GAMMA = 1 + GAMMA * mp.mpf(287) / mp.mpf(1004) if sys.argv[3] == "stats" else mp.mpf(sys.argv[3])
 
 
 def g(e):
