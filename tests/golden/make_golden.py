@@ -107,6 +107,21 @@ if want("midsize"):
          l2=np.array([np.linalg.norm(inner[v]) for v in range(4)]),
          stats0=st0, stats5=np.array(r.stats()), **scal(r.params))
 
+# 5b. BASELINE config 2 itself (thermal 2048x1024) after 1, 2, 5 and 10 steps of the reference (~16 s per step):
+#     every 32nd cell of every variable, the per-variable L2 norms of the full interior, the totals
+if want("config2"):
+    r = rr.ReferenceRun(2048, 1024, "thermal")
+    out = dict(stats_0=np.array(r.stats()), **scal(r.params))
+    done = 0
+    for n in (1, 2, 5, 10):
+        r.evolve(n - done)
+        done = n
+        inner = r.fields.state[:, 2:-2, 2:-2]
+        out[f"sub_{n}"] = inner[:, ::32, ::32].copy()
+        out[f"l2_{n}"] = np.array([np.linalg.norm(inner[v]) for v in range(4)])
+        out[f"stats_{n}"] = np.array(r.stats())
+    save("evolve_thermal_2048x1024_10steps_sub32.npz", **out)
+
 # 6. gravity-wave configuration (extra w-momentum source in every stage, source.py:20-50)
 if want("gravity"):
     r = rr.ReferenceRun(100, 50, "gravity")
