@@ -32,6 +32,8 @@
 // bcs.py:92-148) are rebuilt in the register windows, so halo rows are never read.  A segment
 // recomputes 4 + 2 rows of T1 / T2 on either side (none at a wall).
 #pragma once
+#include <type_traits>
+
 #include "pmw_tma.cuh"
 
 namespace pmw {
@@ -174,9 +176,6 @@ __device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int
 #ifndef PMW_XSWEEP_MINB
 #define PMW_XSWEEP_MINB 3
 #endif
-#ifndef PMW_XSWEEP_DUAL
-#define PMW_XSWEEP_DUAL 0  // 1: both passes of a stage evaluated together (four interface evaluations in flight per lane)
-#endif
 template <int P, int POW_MODE, bool WRITE_TMP, bool HAS_SRC = false, bool DYNAMIC = false>
 #ifdef PMW_XSWEEP_MAXNREG
 __global__ void __maxnreg__(PMW_XSWEEP_MAXNREG)
@@ -281,6 +280,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         for (int s = 0; s < 3; ++s) {
             const int nq = min(P, (rem + 10 - 2 * s) / 64 + 1);
             double keep[4] = {0.0, 0.0, 0.0, 0.0};  // lane 0: its first flux of the pass to the right
+            const uint32_t tdst32 = smem_u32(rowT) + (uint32_t)(s * T::S_ELEMS * sizeof(double));  // T1 / T2 row (+ 2*lane)
             // the five taps of a lane's interface pair in pass q
             auto load_taps = [&](int q, double (&t0)[4], double (&t1)[4], double (&t2)[4], double (&t3)[4], double (&t4)[4]) {
 #pragma unroll
@@ -291,15 +291,13 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 }
             };
             // the pair's two cells from the fluxes of pass q (t2, t3: the cells' forcing values)
-            auto finish_pass = [&](int q, const double (&t2)[4], const double (&t3)[4], const double (&f0)[4],
+            auto finish_pass = [&](auto qc, const double (&t2)[4], const double (&t3)[4], const double (&f0)[4],
                                    const double (&f1)[4]) {
+                constexpr int q = decltype(qc)::value;
                 const int t = 64 * q + 2 * lane + 2;  // tile column of the left cell of the pair
                 const int i = i0 + 64 * q;
                 bool ok = t >= tlo && t < thi;
                 if (s == 2) ok = ok && i < nx;
-                // stage 1 -> T1, stage 2 -> T2 (column t), stage 3 -> HBM
-                double* const dst = (s == 2) ? po + 64 * q + 2 : rowT + s * T::S_ELEMS + 64 * q + 2;
-                const long long dvs = (s == 2) ? a.L.vstride : (long long)FW;
                 // All four variables' updates as ONE straight-line block (eight independent FP64 chains, the
                 // four shuffles in flight together), then the stores; the rare extra stores (periodic images
                 // of the edge columns, state_tmp) sit behind a single branch per pass instead of one per
@@ -310,27 +308,40 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                     const double give = (lane == 0) ? keep[v] : f0[v];
                     const double fr = __shfl_sync(0xffffffffu, give, src_lane);  // flux through the pair's right face
                     keep[v] = f0[v];
-                    double ia = t2[v], ib = t3[v];  // stage 1: the initial state is the forcing state
-                    if (s != 0) {
-                        const Pair in = lds2(rowS + v * FW + 64 * q + 2);
-                        ia = in.a; ib = in.b;
-                    }
+                    // the initial state of the cells: always from the state row (in stage 1 these are the taps t2, t3
+                    // again -- re-reading them costs four loads in one stage of three, selecting between registers
+                    // and loads cost sixteen moves in every stage)
+                    const Pair in = lds2(rowS + v * FW + 64 * q + 2);
                     if (HAS_SRC && v == WMOM) {
                         // gravity-wave forcing (source.py:43-50) of the pair's cells; halo cells of T1 / T2
                         // are periodic images, so they take the forcing of the cell they mirror
                         int iw = i % nx;
                         iw += (iw < 0) ? nx : 0;
                         const double2 g = __ldg(reinterpret_cast<const double2*>(a.src_w + (long long)it.k * nx + iw));
-                        xv[v] = make_double2(cell_update<false, true>(f0[v], f1[v], ia, cds, 0.0, 0.0, dts, g.x),
-                                             cell_update<false, true>(f1[v], fr, ib, cds, 0.0, 0.0, dts, g.y));
+                        xv[v] = make_double2(cell_update<false, true>(f0[v], f1[v], in.a, cds, 0.0, 0.0, dts, g.x),
+                                             cell_update<false, true>(f1[v], fr, in.b, cds, 0.0, 0.0, dts, g.y));
                     } else {
-                        xv[v] = make_double2(cell_update<false, false>(f0[v], f1[v], ia, cds, 0.0, 0.0, dts, 0.0),
-                                             cell_update<false, false>(f1[v], fr, ib, cds, 0.0, 0.0, dts, 0.0));
+                        xv[v] = make_double2(cell_update<false, false>(f0[v], f1[v], in.a, cds, 0.0, 0.0, dts, 0.0),
+                                             cell_update<false, false>(f1[v], fr, in.b, cds, 0.0, 0.0, dts, 0.0));
                     }
                 }
+                // stage 1 -> T1, stage 2 -> T2 (column t): shared memory through a 32-bit address and immediate
+                // offsets; stage 3 -> HBM
+                if (s != 2) {
+                    if (ok) {
+                        constexpr int o = 8 * (64 * q + 2), vs = 8 * FW;
+                        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(tdst32), "n"(o), "d"(xv[0].x), "d"(xv[0].y) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(tdst32), "n"(o + vs), "d"(xv[1].x), "d"(xv[1].y) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(tdst32), "n"(o + 2 * vs), "d"(xv[2].x), "d"(xv[2].y) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(tdst32), "n"(o + 3 * vs), "d"(xv[3].x), "d"(xv[3].y) : "memory");
+                    }
+                    return;
+                }
+                double* const dst = po + 64 * q + 2;
+                const long long dvs = a.L.vstride;
                 if (ok) {
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs) = xv[v];  // generic store: shared or global
+                    for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(dst + v * dvs) = xv[v];
                 }
                 if (s == 2 && ok) {
                     if (a.periodic && (i < SWEEP_HALO || i >= nx - SWEEP_HALO)) {
@@ -349,36 +360,17 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                     }
                 }
             };
-            bool done = false;
-            if constexpr (PMW_XSWEEP_DUAL == 1 && P == 2) if (nq == 2) {
-                // both passes at once: four independent interface evaluations per lane and one fallback vote
-                double a0[4], a1[4], a2[4], a3[4], a4[4], b0[4], b1[4], b2[4], b3[4], b4[4];
-                double fa0[4], fa1[4], fb0[4], fb1[4];
-                load_taps(1, a0, a1, a2, a3, a4);
-                load_taps(0, b0, b1, b2, b3, b4);
-                const bool ba0 = interface_flux_fast<false, POW_MODE>(a0, a1, a2, a3, bg, a.hv_coeff, false, fa0);
-                const bool bb0 = interface_flux_fast<false, POW_MODE>(b0, b1, b2, b3, bg, a.hv_coeff, false, fb0);
-                const bool ba1 = interface_flux_fast<false, POW_MODE>(a1, a2, a3, a4, bg, a.hv_coeff, false, fa1);
-                const bool bb1 = interface_flux_fast<false, POW_MODE>(b1, b2, b3, b4, bg, a.hv_coeff, false, fb1);
-                if (__any_sync(0xffffffffu, ba0 || ba1 || bb0 || bb1)) {
-                    asm volatile("" ::: "memory");
-                    xpair_fix<POW_MODE>(ba0, ba1, a0, a1, a2, a3, a4, bg, a.hv_coeff, fa0, fa1);
-                    xpair_fix<POW_MODE>(bb0, bb1, b0, b1, b2, b3, b4, bg, a.hv_coeff, fb0, fb1);
-                }
-                finish_pass(1, a2, a3, fa0, fa1);
-                finish_pass(0, b2, b3, fb0, fb1);
-                done = true;
-            }
-            if (!done) {
-#pragma unroll
-                for (int q = P - 1; q >= 0; --q) {
-                    if (q >= nq) continue;
-                    double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
-                    load_taps(q, t0, t1, t2, t3, t4);
-                    xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
-                    finish_pass(q, t2, t3, f0, f1);
-                }
-            }
+            auto one_pass = [&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if (q >= nq) return;
+                double t0[4], t1[4], t2[4], t3[4], t4[4], f0[4], f1[4];
+                load_taps(q, t0, t1, t2, t3, t4);
+                xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
+                finish_pass(qc, t2, t3, f0, f1);
+            };
+            if constexpr (P == 3) one_pass(std::integral_constant<int, 2>{});
+            one_pass(std::integral_constant<int, 1>{});
+            one_pass(std::integral_constant<int, 0>{});
             __syncwarp();
             src = rowT + s * T::S_ELEMS;
             dts = (s == 0) ? a.dt2 : a.dt3;
@@ -638,7 +630,8 @@ constexpr int ZS_COLS = 32;   // columns per strip (one per lane)
 constexpr int ZS_RING = 16;   // state rows resident per warp
 constexpr int ZS_AHEAD = 6;   // rows requested ahead of the newest row in use
 constexpr int ZS_ROW = NVAR * ZS_COLS;  // doubles per ring slot
-constexpr size_t zsweep_smem_bytes() { return (size_t)ZS_RING * ZS_ROW * sizeof(double) + ZS_RING * 8; }
+// state ring | interface-profile ring [16][4] (the entry of interface m rides along with state row m) | mbarriers
+constexpr size_t zsweep_smem_bytes() { return (size_t)ZS_RING * (ZS_ROW + 4) * sizeof(double) + ZS_RING * 8; }
 
 // Register window of one stage: the forcing cells k-2 .. k+1 of interface k, [slot][variable].
 // The generic path keeps tap t in slot t and shifts; the steady-state path rotates instead (tap t
@@ -737,17 +730,33 @@ struct ZStage {
 
 struct ZStream {  // per-warp constants of the state-row stream
     double* ring;
+    double* bgring;  // [ZS_RING][4]: {dens, dens_theta, 1/dens_theta, pressure} of interface m in the slot of row m
     uint64_t* bars;
     const CUtensorMap* tm;
+    const double* int_pack;  // Hydro::int_pack
     int f0, last_cell, c0, lane;
     unsigned long long pol;
-    __device__ __forceinline__ void request(int m) const  // lane 0: start the load of state cell row m
+    // lane 0: start the load of state cell row m, and of the hydrostatic profiles of interface m with it (a 32-byte
+    // bulk copy onto the same mbarrier: the steady iterations then read their profiles from shared memory instead
+    // of through L1, whose misses -- one line per 16 interfaces and profile -- were 12 % of the stall samples)
+    __device__ __forceinline__ void request(int m) const
     {
         if (m <= last_cell) {
             const int s = (m - f0) & (ZS_RING - 1);
-            mbar_arrive_expect_tx(bars + s, (uint32_t)(ZS_ROW * sizeof(double)));
+            mbar_arrive_expect_tx(bars + s, (uint32_t)((ZS_ROW + 4) * sizeof(double)));
             tma_load_3d(ring + s * ZS_ROW, tm, c0 + HS + 4, m + HS, 0, bars + s, pol);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];"
+                         ::"r"(smem_u32(bgring + 4 * s)), "l"(int_pack + 4 * (long long)m), "r"(smem_u32(bars + s))
+                         : "memory");
         }
+    }
+    __device__ __forceinline__ IfaceBg bg(int m) const  // profiles of interface m (row m has been waited for)
+    {
+        const double* p = bgring + 4 * ((m - f0) & (ZS_RING - 1));
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        IfaceBg r;
+        r.dens = a.x; r.dens_theta = a.y; r.inv_dens_theta = b.x; r.pressure = b.y;
+        return r;
     }
     __device__ __forceinline__ const double* row(int m) const
     {
@@ -775,7 +784,7 @@ __device__ __forceinline__ void zsweep_steady(const SweepArgs& a, const ZStream&
 #pragma unroll
     for (int v = 0; v < 4; ++v)
         s1.W[R & 3][v] = top[v * ZS_COLS];  // newest state row replaces the oldest: taps now start at slot R+1
-    const IfaceBg bg1 = bg_z(a.hy, j), bg2 = bg_z(a.hy, j - 3), bg3 = bg_z(a.hy, j - 6);
+    const IfaceBg bg1 = zs.bg(j), bg2 = zs.bg(j - 3), bg3 = zs.bg(j - 6);
     const bool bad3 = s3.template flux_fast<R>(a, bg3, f3);
     const bool bad2 = s2.template flux_fast<R>(a, bg2, f2);
     const bool bad1 = s1.template flux_fast<R + 1>(a, bg1, f1);
@@ -841,7 +850,9 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ZStream zs;
     zs.ring = reinterpret_cast<double*>(smem_raw);
-    zs.bars = reinterpret_cast<uint64_t*>(zs.ring + ZS_RING * ZS_ROW);
+    zs.bgring = zs.ring + ZS_RING * ZS_ROW;
+    zs.bars = reinterpret_cast<uint64_t*>(zs.bgring + ZS_RING * 4);
+    zs.int_pack = a.hy.int_pack;
     zs.tm = &tm_row;
 
     const int lane = threadIdx.x;
