@@ -228,7 +228,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     {
         // 8 profile tables + the packed interface table Hydro::int_pack (32-byte aligned, hence the slack)
         const size_t nhy = (size_t)4 * (params->nz + 4) + (size_t)4 * (params->nz + 1) + 4 +
-                           (size_t)4 * (params->nz + 1 + 2 * HY_PACK_PAD);
+                           (size_t)4 * (params->nz + 1 + 2 * HY_PACK_PAD) + (size_t)4 * (params->nz + 4);
         if (cudaMalloc(&c->hydro_blob, nhy * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_partial, (size_t)2 * c->stats_blocks * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess ||
@@ -391,7 +391,8 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
          "pmw_set_hydrostatic: null profile");
     const int ncell = c->p.nz + 4, nint = c->p.nz + 1, npack = nint + 2 * HY_PACK_PAD;
     const size_t pack_off = ((size_t)4 * ncell + (size_t)4 * nint + 3) / 4 * 4;  // 32-byte aligned (cudaMalloc base is)
-    std::vector<double> h(pack_off + (size_t)4 * npack);
+    const size_t cpack_off = pack_off + (size_t)4 * npack;
+    std::vector<double> h(cpack_off + (size_t)4 * ncell);
     double* q = h.data();
     double* o_dc = q;            q += ncell;
     double* o_dtc = q;           q += ncell;
@@ -431,6 +432,10 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
         o_pack[4 * j + 2] = o_idti[k];
         o_pack[4 * j + 3] = o_pi[k];
     }
+    for (int k = 0; k < ncell; ++k) {
+        double* e = h.data() + cpack_off + 4 * (size_t)k;
+        e[0] = o_dc[k]; e[1] = o_dtc[k]; e[2] = o_idtc[k]; e[3] = o_pc[k];
+    }
     CU_TRY(cudaMemcpyAsync(c->hydro_blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     double* d = c->hydro_blob;
@@ -443,6 +448,8 @@ extern "C" int pmw_set_hydrostatic(pmw_ctx* c, const double* dens_cell, const do
     c->hy.pressure_int = d;             d += nint;
     c->hy.inv_dens_theta_int = d;
     c->hy.int_pack = c->hydro_blob + pack_off + (size_t)4 * HY_PACK_PAD;
+    c->hy.cell_pack = c->hydro_blob + cpack_off;
+    c->hy.pad_ = nullptr;
     c->hydro_set = true;
     return PMW_OK;
 }

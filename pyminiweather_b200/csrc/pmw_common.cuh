@@ -56,6 +56,10 @@ struct Hydro {
     // interfaces -HY_PACK_PAD .. nz+HY_PACK_PAD (clamped copies beyond the domain): int_pack[4*k + 0..3];
     // 32-byte aligned entries, so that a z sweep can pull them into shared memory with bulk copies
     const double* int_pack;
+    // the four cell-row profiles of the x sweeps interleaved the same way, {dens, dens_theta, 1/dens_theta,
+    // C0*dens_theta^gamma} per array row: cell_pack[4*k + 0..3], k in [0, nz+4)
+    const double* cell_pack;
+    const double* pad_;  // keeps the members that follow a Hydro in the kernel argument structs on their 16-byte alignment
 };
 constexpr int HY_PACK_PAD = 8;
 

@@ -119,7 +119,8 @@ struct XSweepTile {
     static constexpr int WARPS = PMW_XSWEEP_WARPS;  // per CTA (no block-level synchronisation: any number works)
     static constexpr int S_ELEMS = NVAR * FW;
     static constexpr int WARP_ELEMS = 4 * S_ELEMS;  // S[2] (double-buffered state row), T1, T2
-    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16); }
+    // per warp: the four row buffers, two mbarriers, and the hydrostatic profiles of the two rows in flight (2 x 32 B)
+    static constexpr size_t smem_bytes() { return (size_t)WARPS * (WARP_ELEMS * sizeof(double) + 16 + 64); }
 };
 
 // Both interface fluxes of a lane's pair with ONE warp-uniform fallback branch (see
@@ -191,6 +192,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     double* const sS = reinterpret_cast<double*>(smem_raw) + warp * T::WARP_ELEMS;
     double* const sT = sS + 2 * T::S_ELEMS;  // T1, then T2
     uint64_t* const bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + T::WARPS * T::WARP_ELEMS) + 2 * warp;
+    double* const sBg = reinterpret_cast<double*>(smem_raw) + T::WARPS * (T::WARP_ELEMS + 2) + 8 * warp;  // [2][4]
     static_assert((T::S_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
 
     const int nx = a.L.nx, nz = a.L.nz;
@@ -221,9 +223,13 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
             if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old row before the TMA write
-        mbar_arrive_expect_tx(bars + buf, (uint32_t)(T::S_ELEMS * sizeof(double)));
+        mbar_arrive_expect_tx(bars + buf, (uint32_t)((T::S_ELEMS + 4) * sizeof(double)));
         // map column 0 is interior column -6 (array column -4)
         tma_load_3d(sS + buf * T::S_ELEMS, &tm_row, it.c0, it.k + HS, 0, bars + buf, pol);
+        // the row's hydrostatic profiles ride along (32 bytes of Hydro::cell_pack onto the same mbarrier)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 32, [%2];"
+                     ::"r"(smem_u32(sBg + 4 * buf)), "l"(a.hy.cell_pack + 4 * (long long)(it.k + HS)), "r"(smem_u32(bars + buf))
+                     : "memory");
     };
     const int src_lane = (lane + 1) & 31;
     int buf = 0;
@@ -261,7 +267,6 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         }
         if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nz, ntx, T::LC, a.edge_last), buf ^ 1);
         n = n_next;
-        const IfaceBg bg = bg_x(a.hy, it.k + HS);
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
         const int rem = min(nx - it.c0, T::LC);
@@ -272,6 +277,11 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         const int i0 = it.c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
         mbar_wait(bars + buf, (phase >> buf) & 1);
         phase ^= 1u << buf;
+        IfaceBg bg;
+        {
+            const double2 b01 = *reinterpret_cast<const double2*>(sBg + 4 * buf), b23 = *reinterpret_cast<const double2*>(sBg + 4 * buf + 2);
+            bg.dens = b01.x; bg.dens_theta = b01.y; bg.inv_dens_theta = b23.x; bg.pressure = b23.y;
+        }
 
         const double* src = rowS;  // forcing row of the stage (+ 2*lane)
         double dts = a.dt1, cds = a.cd1;
@@ -646,8 +656,8 @@ struct ZStage {
     // finalise cell k-1 = init + dt*tendency.
     // HAS_SRC: `src` is the gravity-wave forcing (source.py:43-50) of cell k-1.
     template <bool HAS_SRC = false>
-    __device__ __forceinline__ void step(const SweepArgs& a, int k, double dt_stage, double cd, double cg,
-                                         const double (&init)[4], double (&cell)[4], double src = 0.0)
+    __device__ __forceinline__ void step(const SweepArgs& a, int k, const IfaceBg& bg, double dt_stage, double cd,
+                                         double cg, const double (&init)[4], double (&cell)[4], double src = 0.0)
     {
         const int nz = a.L.nz;
         const double* hd = a.hy.dens_cell;
@@ -673,7 +683,6 @@ struct ZStage {
             }
         }
         const bool wall = (k == 0 || k == nz);
-        const IfaceBg bg = bg_z(a.hy, k);
         double f[4];
         interface_flux<true, POW_MODE>(W[0], W[1], W[2], W[3], bg, a.hv_coeff, wall, f);
 #pragma unroll
@@ -946,7 +955,7 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
         if (k3 >= lo3 && k3 <= hi3) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) in3[v] = (k3 > lo3) ? zs.row(k3 - 1)[v * ZS_COLS] : 0.0;
-            s3.template step<HAS_SRC>(a, k3, a.dt3, a.cd3, a.cg3, in3, c3, zsrc(k3 - 1));
+            s3.template step<HAS_SRC>(a, k3, zs.bg(k3), a.dt3, a.cd3, a.cg3, in3, c3, zsrc(k3 - 1));
             if (k3 > lo3 && col_ok) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -961,9 +970,9 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
         if (k2 >= lo2 && k2 <= hi2) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) in2[v] = (k2 > lo2) ? zs.row(k2 - 1)[v * ZS_COLS] : 0.0;
-            s2.template step<HAS_SRC>(a, k2, a.dt2, a.cd2, a.cg2, in2, c2, zsrc(k2 - 1));
+            s2.template step<HAS_SRC>(a, k2, zs.bg(k2), a.dt2, a.cd2, a.cg2, in2, c2, zsrc(k2 - 1));
         }
-        if (k1 <= hi1) s1.template step<HAS_SRC>(a, k1, a.dt1, a.cd1, a.cg1, s1.W[1], c1, zsrc(k1 - 1));
+        if (k1 <= hi1) s1.template step<HAS_SRC>(a, k1, zs.bg(k1), a.dt1, a.cd1, a.cg1, s1.W[1], c1, zsrc(k1 - 1));
         s3.push(c2);
         s2.push(c1);
         ++j;

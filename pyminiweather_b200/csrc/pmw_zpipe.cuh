@@ -268,7 +268,8 @@ sweep_z3(const __grid_constant__ CUtensorMap tm_rows, const SweepArgs a)
 #pragma unroll
                     for (int v = 0; v < 4; ++v) in[v] = z3_lds<0>(pin + 8u * v * Z3_VS, tok);
                 }
-                st.template step<HAS_SRC>(a, j, dts, cds, cgs, in, c, zsrc(j - 1));
+                st.template step<HAS_SRC>(a, j, z3_lds_bg<0>(bgring + 32u * ((j - f0) & (Z3_SRING - 1)), tok), dts, cds, cgs, in, c,
+                                           zsrc(j - 1));
                 if (j > lo) {
                     if (to_hbm) {
                         double* q = dhbm + (long long)(j - 1) * pitch;
