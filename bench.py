@@ -390,9 +390,19 @@ class Bench:
         ev1.record(self.stream)
         sync()
         ck = sampler.stop() if sampler else None
+        if ck is not None and collective and self.world > 1:  # every rank's clocks: a ring runs at the pace of its slowest GPU
+            allck = [None] * self.world
+            self.dist.all_gather_object(allck, {"sm_mhz": ck["sm_mhz"], "reasons": ck["reasons"], "power_w_max": ck["power_w_max"]})
+            ck["by_rank"] = allck
         ms = ev0.elapsed_time(ev1)
         launches = solver.launch_count - l0
+        self.last_ms_by_rank = [ms]
         if collective:
+            if self.world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                allt = [torch.empty_like(t) for _ in range(self.world)]
+                self.dist.all_gather(allt, t)
+                self.last_ms_by_rank = [float(x.item()) for x in allt]
             ms, launches = self.max_over_ranks(ms), int(self.sum_over_ranks(launches))
         if ring is not None:
             ring.check()  # raises if a halo wait ever timed out
@@ -433,13 +443,16 @@ def run_extra_configs(b, fp64_peak):
             ring = b.make_ring(solver, world, rank)
             # two timed repetitions of the K steps: the shorter one is the figure (a one-off host stall on any rank of
             # the ring shows up in a 60-150 ms region; both are kept in `ms_per_step_runs`)
-            runs = [b.time_steps(solver, ring, steps, 10, clocks=True) for _ in range(2)]
+            runs, by_rank = [], []
+            for _ in range(2):
+                runs.append(b.time_steps(solver, ring, steps, 10, clocks=True))
+                by_rank.append([t / steps for t in b.last_ms_by_rank])
             ms, launches, ck = min(runs, key=lambda r: r[0])
             finite = _finite_stats(ring.stats() if ring else solver.stats())
             solver.close()
             cells = nxl * world * nz
             rec.update(nx=nxl * world, nz=nz, nx_per_gpu=nxl, steps=steps, ms_per_step=ms / steps,
-                       ms_per_step_runs=[r[0] / steps for r in runs],
+                       ms_per_step_runs=[r[0] / steps for r in runs], ms_per_step_by_rank=by_rank,
                        value=cells * steps / (ms * 1e-3), unit=UNIT, gpu_launches=launches, clocks=ck,
                        state_finite_after_run=finite,
                        fp64_frac=_fp64_rate(cells, steps, ms) / fp64_peak / world if fp64_peak else None)

@@ -1220,7 +1220,8 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         }                                                                                               \
         const int ncta = (int)std::min<long long>((long long)nsm * per_sm[c->p.device & 63],            \
                                                   (nitems + T::WARPS - 1) / T::WARPS);                  \
-        const int npush = a.push_epoch ? std::min(ncta, 8) : 0;                                         \
+        /* CTAs that push the edge columns first: enough of them that the push of a tall slab ends early */  \
+        const int npush = a.push_epoch ? std::max(1, std::min(ncta / 2, std::max(8, c->p.nz / 128))) : 0; \
         const dim3 grid(ncta);                                                                          \
         a.item_counter = dyn_items ? c->xitem_counter : nullptr;                                        \
         a.item_base = c->xitem_base;                                                                    \

@@ -152,7 +152,7 @@ __device__ __forceinline__ double cell_energy(double dens, double mu, double mw,
     return fma(mu, mu, mw * mw) / rho + ie;  // no 1/2 on the kinetic term (stats.py:27)
 }
 
-// Pass 1: items = (row, chunk of 512 columns), grid-stride; 16-byte loads (interior column 0 sits on a
+// Pass 1: items = (row, chunk of 1024 columns), grid-stride; 16-byte loads (interior column 0 sits on a
 // 128-byte line, pmw_common.cuh), row constants hoisted, per-thread sums, warp-shuffle tree, one partial per
 // block.  partial[2*b] = sum rho, [2*b+1] = sum(ke+ie).  HBM-bound: 32 B per cell.
 __global__ void __launch_bounds__(256) stats_partial_kernel(const double* __restrict__ s, const Layout L,
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const double* __rest
                                                             const double* __restrict__ pcell, const double kconst,
                                                             double* partial)
 {
-    constexpr int CHUNK = 512;  // columns per item: one double2 per thread
+    constexpr int CHUNK = 1024;  // columns per item: two double2 per thread and variable, all eight loads in flight
     const int nchunks = (L.nx + CHUNK - 1) / CHUNK;
     const int nitems = L.nz * nchunks;
     const double k_c0 = kconst * C0;
@@ -176,20 +176,30 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const double* __rest
         const double* p = s + idx(L, 0, k + HS, i + HS);
         double r0, r1;
         if (vec) {
-            const double2 d = *reinterpret_cast<const double2*>(p);
-            const double2 u = *reinterpret_cast<const double2*>(p + L.vstride);
-            const double2 w = *reinterpret_cast<const double2*>(p + 2 * L.vstride);
-            const double2 t = *reinterpret_cast<const double2*>(p + 3 * L.vstride);
+            const bool two = i + CHUNK / 2 < L.nx;  // the thread's second pair, 512 columns further
+            const double* p2 = p + (two ? CHUNK / 2 : 0);
+            const double2 d = *reinterpret_cast<const double2*>(p), d2 = *reinterpret_cast<const double2*>(p2);
+            const double2 u = *reinterpret_cast<const double2*>(p + L.vstride), u2 = *reinterpret_cast<const double2*>(p2 + L.vstride);
+            const double2 w = *reinterpret_cast<const double2*>(p + 2 * L.vstride), w2 = *reinterpret_cast<const double2*>(p2 + 2 * L.vstride);
+            const double2 t = *reinterpret_cast<const double2*>(p + 3 * L.vstride), t2 = *reinterpret_cast<const double2*>(p2 + 3 * L.vstride);
             energy += cell_energy(d.x, u.x, w.x, t.x, h, ht, iht, kp, k_c0, r0);
             energy += cell_energy(d.y, u.y, w.y, t.y, h, ht, iht, kp, k_c0, r1);
             mass += r0 + r1;
+            if (two) {
+                energy += cell_energy(d2.x, u2.x, w2.x, t2.x, h, ht, iht, kp, k_c0, r0);
+                energy += cell_energy(d2.y, u2.y, w2.y, t2.y, h, ht, iht, kp, k_c0, r1);
+                mass += r0 + r1;
+            }
         } else {
-            energy += cell_energy(p[0], p[L.vstride], p[2 * L.vstride], p[3 * L.vstride], h, ht, iht, kp, k_c0, r0);
-            mass += r0;
-            if (i + 1 < L.nx) {
-                energy += cell_energy(p[1], p[L.vstride + 1], p[2 * L.vstride + 1], p[3 * L.vstride + 1], h, ht, iht, kp,
-                                      k_c0, r1);
-                mass += r1;
+            for (int ii = i; ii < min(i + CHUNK / 2 + 2, L.nx); ii += CHUNK / 2) {
+                const double* q = s + idx(L, 0, k + HS, ii + HS);
+                energy += cell_energy(q[0], q[L.vstride], q[2 * L.vstride], q[3 * L.vstride], h, ht, iht, kp, k_c0, r0);
+                mass += r0;
+                if (ii + 1 < L.nx) {
+                    energy += cell_energy(q[1], q[L.vstride + 1], q[2 * L.vstride + 1], q[3 * L.vstride + 1], h, ht, iht, kp,
+                                          k_c0, r1);
+                    mass += r1;
+                }
             }
         }
     }

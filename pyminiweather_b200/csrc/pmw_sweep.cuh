@@ -79,14 +79,30 @@ __device__ __forceinline__ void push_halo6_role(const SweepArgs& a, int npush)
     const int tid = threadIdx.x, nthr = blockDim.x;
     const Layout& L = a.L;
     const int per_row = SWEEP_HALO / 2;  // column pairs per side
-    for (int t = blockIdx.x * nthr + tid; t < NVAR * L.nz * per_row; t += npush * nthr) {
-        const int j = t % per_row, k = (t / per_row) % L.nz, v = t / (per_row * L.nz);
-        const double2 first = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, HS + 2 * j));
-        const double2 last =
-            *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, L.nx + HS - SWEEP_HALO + 2 * j));
-        // our first columns are the left neighbour's right halo; our last columns the right neighbour's left halo
-        *reinterpret_cast<double2*>(a.nbr_state_left + idx(L, v, k + HS, L.nx + HS + 2 * j)) = first;
-        *reinterpret_cast<double2*>(a.nbr_state_right + idx(L, v, k + HS, HS - SWEEP_HALO + 2 * j)) = last;
+    const int total = NVAR * L.nz * per_row, stride = npush * nthr;
+    // four elements per thread and iteration, loads first: the loop is bound by the latency of its (cold, 48-byte)
+    // reads, and the epoch cannot be published before the last of them -- with one element in flight per thread a
+    // 4096 x 8192 slab took ~0.9 ms to push and the neighbours' edge tiles waited for it (profiles/r2v)
+    for (int t0 = blockIdx.x * nthr + tid; t0 < total; t0 += 4 * stride) {
+        double2 first[4], last[4];
+        long long ol[4], orr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = min(t0 + u * stride, total - 1);
+            const int j = t % per_row, k = (t / per_row) % L.nz, v = t / (per_row * L.nz);
+            first[u] = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, HS + 2 * j));
+            last[u] = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, L.nx + HS - SWEEP_HALO + 2 * j));
+            // our first columns are the left neighbour's right halo; our last columns the right neighbour's left halo
+            ol[u] = idx(L, v, k + HS, L.nx + HS + 2 * j);
+            orr[u] = idx(L, v, k + HS, HS - SWEEP_HALO + 2 * j);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (t0 + u * stride < total) {
+                *reinterpret_cast<double2*>(a.nbr_state_left + ol[u]) = first[u];
+                *reinterpret_cast<double2*>(a.nbr_state_right + orr[u]) = last[u];
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();

@@ -53,7 +53,7 @@ static_assert(Z3_AHEAD <= 16 && Z3_AHEAD % 4 == 0, "state ring too small for thi
 
 // The three warps meet here: a named barrier with an explicit thread count.
 // `tok` orders the ring loads below (plain asm, free to be scheduled) after the barrier they follow.
-__device__ __forceinline__ void z3_barrier(uint32_t& tok) { asm volatile("bar.sync 1, 96;" : "+r"(tok) : : "memory"); }
+__device__ __forceinline__ void z3_barrier(uint32_t& tok) { asm volatile("barrier.sync 1, 96;" : "+r"(tok) : : "memory"); }
 // Ring accesses by 32-bit shared-window address (+ a compile-time byte offset): the compiler neither
 // re-derives the window base from a generic pointer nor carries 64-bit addresses for them.
 template <int OFF>

@@ -28,7 +28,8 @@ for variant in ("tma", "direct"):
         if variant == "tma":  # the other sweep organisations: transposing z sweep, stage-by-stage kernels
             _, c2 = new_case(nx, nz, "collision")
             no.evolve(c2); no.evolve(c2); no.evolve(c2)
-            for tune in (dict(fuse=1, sweep_zt=1), dict(fuse=1, sweep_zt=0, sweep_lz=9), dict(fuse=0)):
+            for tune in (dict(fuse=1, sweep_zt=1), dict(fuse=1, sweep_zt=0, sweep_lz=9), dict(fuse=1, sweep_z3=1, sweep_lz=9),
+                         dict(fuse=0)):
                 t = DeviceSolver(nx, nz, case.dx, case.dz, case.dt, variant=variant)
                 t.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); t.set_tuning(**tune)
                 _, c0 = new_case(nx, nz, "collision")
@@ -38,4 +39,35 @@ for variant in ("tma", "direct"):
                 print("  ", tune, "err %.2e" % e2, flush=True)
                 assert e2 < 1e-11
                 t.close()
+# kernels added later: gravity-wave forcing in the fused sweeps (HAS_SRC), the injection inflow fill, the device-side
+# init, the pow() fallbacks inside the fused sweeps (cold call / bail-out to the generic iteration), the diagnostics
+# kernel on an odd width, the FP64 probe
+from helpers import synthetic_case
+p, case = new_case(130, 33, "gravity")
+for tune in (dict(fuse=1, sweep_lz=9), dict(fuse=1, sweep_z3=1, sweep_lz=9)):
+    s = DeviceSolver(130, 33, case.dx, case.dz, case.dt)
+    s.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); s.set_tuning(**tune); s.set_source_w(case.source_w)
+    s.upload(0, case.state); s.upload(1, case.state_tmp); s.evolve(3); print("gravity", tune, s.stats(0), flush=True); s.close()
+from pyminiweather_b200.data import initialize_fields
+from pyminiweather_b200.ics import init_device
+from pyminiweather_b200.mesh import MeshData
+from pyminiweather_b200.solve import evolve
+from helpers import make_params
+for ic in ("injection", "collision"):
+    pp = make_params(64, 32, ic)
+    f = initialize_fields(pp); m = MeshData(pp); init_device(f, pp, m)
+    for _ in range(3):
+        evolve(pp, f, m, dt=pp["dt"])
+    print(ic, "device init + evolve", float(np.abs(f.state).max()), flush=True); f.close()
+p, case = synthetic_case(150, 40, seed=5)
+case.state[3, 10:25, 20:90] += 0.2 * case.hy_dens_theta_cell[10:25, None]
+case.state_tmp[:] = case.state
+for tune in (dict(fuse=1, sweep_lz=16), dict(fuse=1, sweep_z3=1, sweep_lz=16), dict(fuse=1, sweep_zt=1)):
+    s = DeviceSolver(150, 40, case.dx, case.dz, case.dt)
+    s.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); s.set_tuning(**tune)
+    s.upload(0, case.state); s.upload(1, case.state_tmp); s.evolve(2); print("pow fallback", tune, s.stats(0), flush=True); s.close()
+p, case = synthetic_case(101, 37, seed=2)
+s = DeviceSolver(101, 37, case.dx, case.dz, case.dt, variant="direct")
+s.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); s.upload(0, case.state); s.upload(1, case.state_tmp)
+print("stats odd nx", s.stats(0), "fp64 probe", s.fp64_peak(), flush=True); s.close()
 print("sanitize case ok")
