@@ -394,9 +394,11 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
                 xpair_flux<POW_MODE>(t0, t1, t2, t3, t4, bg, a.hv_coeff, f0, f1);
                 finish_pass(qc, t2, t3, f0, f1);
             };
-            if constexpr (P == 3) one_pass(std::integral_constant<int, 2>{});
-            one_pass(std::integral_constant<int, 1>{});
-            one_pass(std::integral_constant<int, 0>{});
+            {
+                if constexpr (P == 3) one_pass(std::integral_constant<int, 2>{});
+                one_pass(std::integral_constant<int, 1>{});
+                one_pass(std::integral_constant<int, 0>{});
+            }
             __syncwarp();
             src = rowT + s * T::S_ELEMS;
             dts = (s == 0) ? a.dt2 : a.dt3;

@@ -55,6 +55,15 @@ for spec in sys.argv[1:]:
     if rank == 0:
         s1 = make(True); t1 = timed(s1, None, steps, False); s1.close()
     dist.barrier()
+    # a second single-GPU figure: the same slab as a ring of ONE mapped onto itself (all of the protocol, no NVLink),
+    # measured on every rank at the same time (do the GPUs of the box disturb each other?)
+    s2 = make(False)
+    mine = s2.local_ptrs(); s2.connect_peers(mine, mine)
+    t_self = timed(s2, None, steps, False); s2.close()
+    ts = torch.tensor([t_self], dtype=torch.float64, device="cuda")
+    allts = [torch.empty_like(ts) for _ in range(world)]
+    dist.all_gather(allts, ts)
     if rank == 0:
-        print(f"{nx}x{nz} per GPU {tune}: ring of {world} {tn*1e3:8.1f} us/step   alone {t1*1e3:8.1f} us/step   efficiency {t1/tn:.3f}", flush=True)
+        print(f"{nx}x{nz} per GPU {tune}: ring of {world} {tn*1e3:8.1f} us/step   alone {t1*1e3:8.1f} us/step   efficiency {t1/tn:.3f}   "
+              f"self-ring on every rank simultaneously: {[round(float(x.item())*1e3, 1) for x in allts]}", flush=True)
 dist.destroy_process_group()
