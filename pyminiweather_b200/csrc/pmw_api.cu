@@ -78,6 +78,7 @@ struct pmw_ctx {
     bool xhalo6_valid[3];  // ... and so do the four further columns a fused x sweep reads (6-wide image)
     // fused sweeps (pmw_sweep.cuh): 1 = pmw_evolve runs one kernel per directional sweep
     int fuse, keep_tmp, sweep_lz, sweep_xp, sweep_zt, sweep_z3, dyn_items;
+    long long push_all_cells;  // slab ring: from this many cells per slab on, every CTA of an x sweep takes part in the halo push
     double* hydro_blob;
     double* src_w;  // gravity-wave forcing field or nullptr
     unsigned char* jet_rows;  // injection: [nz] mask of the inflow rows, or nullptr (periodic x)
@@ -204,6 +205,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->keep_tmp = 1;
     c->sweep_lz = 0;  // 0 = choose from the grid (pick_sweep_lz)
     c->sweep_xp = 2;
+    c->push_all_cells = 0;  // never (measured worse: every CTA then waits for its peer stores, profiles/r2ae)
     c->dyn_items = 1;  // x sweeps of a slab ring draw their items from a counter (0 never, 2 always)
     c->sweep_z3 = 0;  // z sweeps: 1 = stage-pipelined CTA of three warps (pmw_zpipe.cuh), 0 = one warp per strip (sweep_z)
     c->sweep_zt = 0;  // z sweeps: 0 = streaming kernel (72 us at 2048x1024), 1 = transposing x-style kernel (90 us)
@@ -232,8 +234,10 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
         if (cudaMalloc(&c->hydro_blob, nhy * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_partial, (size_t)2 * c->stats_blocks * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&c->stats_out, 2 * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&c->flags, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMemset(c->flags, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+            // slab ring: the flag words, and behind them (one allocation = one IPC handle) the staging area the
+            // neighbours push their edge columns into (pmw_sweep.cuh: halo_stage)
+            cudaMalloc(&c->flags, halo_stage_bytes(params->nz)) != cudaSuccess ||
+            cudaMemset(c->flags, 0, halo_stage_bytes(params->nz)) != cudaSuccess ||
             cudaMalloc(&c->xitem_counter, sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(c->xitem_counter, 0, sizeof(unsigned long long)) != cudaSuccess ||
             cudaMalloc(&c->edge_counters, 2 * sizeof(unsigned int)) != cudaSuccess ||
@@ -350,6 +354,9 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
     } else if (!strcmp(key, "sweep_xp")) {
         NEED(value == 2 || value == 3, "sweep_xp must be 2 or 3");
         c->sweep_xp = value;
+    } else if (!strcmp(key, "push_all_mcells")) {
+        NEED(value >= 0, "push_all_mcells must be >= 0 (0: never)");
+        c->push_all_cells = (long long)value << 20;
     } else if (!strcmp(key, "dyn_items")) {
         NEED(value >= 0 && value <= 2, "dyn_items must be 0, 1 or 2");
         c->dyn_items = value;
@@ -375,6 +382,7 @@ extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
     else if (!strcmp(key, "sweep_zt")) *value = c->sweep_zt;
     else if (!strcmp(key, "sweep_z3")) *value = c->sweep_z3;
     else if (!strcmp(key, "dyn_items")) *value = c->dyn_items;
+    else if (!strcmp(key, "push_all_mcells")) *value = (int)(c->push_all_cells >> 20);
     else return fail(PMW_EINVAL, "pmw_get_tuning: unknown key '%s'", key);
     return PMW_OK;
 }
@@ -1221,7 +1229,10 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         const int ncta = (int)std::min<long long>((long long)nsm * per_sm[c->p.device & 63],            \
                                                   (nitems + T::WARPS - 1) / T::WARPS);                  \
         /* CTAs that push the edge columns first: enough of them that the push of a tall slab ends early */  \
-        const int npush = a.push_epoch ? std::max(1, std::min(ncta / 2, std::max(8, c->p.nz / 128))) : 0; \
+        /* big slabs (sweep of several 100 us): EVERY CTA pushes its share before its first item, while the memory */ \
+        /* system is still idle -- a few us per CTA; pushes issued next to running tiles were served late (r2z)   */ \
+        const bool push_all = (long long)c->p.nx * c->p.nz >= (c->push_all_cells > 0 ? c->push_all_cells : (1ll << 62));   \
+        const int npush = !a.push_epoch ? 0 : push_all ? ncta : std::max(1, std::min(ncta / 2, std::max(8, c->p.nz / 128))); \
         const dim3 grid(ncta);                                                                          \
         a.item_counter = dyn_items ? c->xitem_counter : nullptr;                                        \
         a.item_base = c->xitem_base;                                                                    \

@@ -72,8 +72,27 @@ struct SweepArgs {
     unsigned long long item_base;
 };
 
-// Slab ring, fused x sweep: the first row of CTAs stores this slab's own six edge columns of S
-// into the neighbours' halo columns and publishes push_epoch (cf. push_halo_role).
+// Slab ring, fused x sweep: where the halo columns travel.  Every context owns a STAGING area behind its flag words
+// (same allocation, so the neighbours reach it through the IPC mapping of the flags):
+//     halo_stage[parity][side][variable][row][6 columns]   doubles, dense;   side 0: my left halo, 1: my right halo
+// The neighbours WRITE it (push_halo6_role, contiguous 16-byte stores: full 128-byte lines over NVLink -- the
+// strided 48-byte pieces of the state array's own halo columns cost 16 x as many packets and made the push of a
+// tall slab last longer than the sweep), the edge tiles of the x sweep READ it (halo_patch_row) into their
+// shared-memory row after the neighbour's epoch has arrived.  Two parities: a neighbour may already push sweep e+1
+// while this slab still reads sweep e, never e+2 (it needs this slab's epoch e+1 to get there).
+constexpr int HALO_STAGE_HEADER = 16;  // u64 words in front of the staging area (flags[0..3] + padding: 128 bytes)
+__host__ __device__ inline size_t halo_stage_bytes(int nz)
+{
+    return HALO_STAGE_HEADER * sizeof(unsigned long long) + (size_t)2 * 2 * NVAR * nz * SWEEP_HALO * sizeof(double);
+}
+__device__ __forceinline__ double* halo_stage(unsigned long long* flags, int nz, unsigned long long epoch, int side)
+{
+    return reinterpret_cast<double*>(flags + HALO_STAGE_HEADER) +
+           ((size_t)(epoch & 1) * 2 + side) * ((size_t)NVAR * nz * SWEEP_HALO);
+}
+
+// The first CTAs of an x sweep store this slab's own six edge columns of S into the neighbours' staging areas
+// and publish push_epoch (cf. push_halo_role).
 __device__ __forceinline__ void push_halo6_role(const SweepArgs& a, int npush)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -81,26 +100,25 @@ __device__ __forceinline__ void push_halo6_role(const SweepArgs& a, int npush)
     const int per_row = SWEEP_HALO / 2;  // column pairs per side
     const int total = NVAR * L.nz * per_row, stride = npush * nthr;
     // four elements per thread and iteration, loads first: the loop is bound by the latency of its (cold, 48-byte)
-    // reads, and the epoch cannot be published before the last of them -- with one element in flight per thread a
-    // 4096 x 8192 slab took ~0.9 ms to push and the neighbours' edge tiles waited for it (profiles/r2v)
+    // reads, and the epoch cannot be published before the last store is acknowledged
+    // our first columns are the left neighbour's RIGHT halo (side 1); our last columns the right neighbour's LEFT halo
+    double2* const to_left = reinterpret_cast<double2*>(halo_stage(a.nbr_flags_left, L.nz, a.push_epoch, 1));
+    double2* const to_right = reinterpret_cast<double2*>(halo_stage(a.nbr_flags_right, L.nz, a.push_epoch, 0));
     for (int t0 = blockIdx.x * nthr + tid; t0 < total; t0 += 4 * stride) {
         double2 first[4], last[4];
-        long long ol[4], orr[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int t = min(t0 + u * stride, total - 1);
+            const int t = min(t0 + u * stride, total - 1);  // t = (v * nz + k) * 3 + j: the staging index itself
             const int j = t % per_row, k = (t / per_row) % L.nz, v = t / (per_row * L.nz);
             first[u] = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, HS + 2 * j));
             last[u] = *reinterpret_cast<const double2*>(a.state + idx(L, v, k + HS, L.nx + HS - SWEEP_HALO + 2 * j));
-            // our first columns are the left neighbour's right halo; our last columns the right neighbour's left halo
-            ol[u] = idx(L, v, k + HS, L.nx + HS + 2 * j);
-            orr[u] = idx(L, v, k + HS, HS - SWEEP_HALO + 2 * j);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (t0 + u * stride < total) {
-                *reinterpret_cast<double2*>(a.nbr_state_left + ol[u]) = first[u];
-                *reinterpret_cast<double2*>(a.nbr_state_right + orr[u]) = last[u];
+            const int t = t0 + u * stride;
+            if (t < total) {
+                to_left[t] = first[u];
+                to_right[t] = last[u];
             }
         }
     }
@@ -234,10 +252,6 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
 
     const unsigned long long pol = l2_policy(1);
     auto request = [&](const XItem& it, int buf) {  // lane 0: start the load of the item's state row
-        if (a.wait_epoch) {
-            if (it.c0 < SWEEP_HALO) wait_epoch(a.flags, 0, a.wait_epoch);
-            if (it.c0 + T::LC + SWEEP_HALO > nx) wait_epoch(a.flags, 1, a.wait_epoch);
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old row before the TMA write
         mbar_arrive_expect_tx(bars + buf, (uint32_t)((T::S_ELEMS + 4) * sizeof(double)));
         // map column 0 is interior column -6 (array column -4)
@@ -293,6 +307,29 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         const int i0 = it.c0 - SWEEP_HALO + 2 * lane + 2;  // interior column of this lane's pair in pass 0
         mbar_wait(bars + buf, (phase >> buf) & 1);
         phase ^= 1u << buf;
+        if (a.wait_epoch) {
+            // slab ring: the TMA box brought whatever the state array holds in its halo columns; the real halo cells
+            // of an edge tile come from the neighbours' pushes (staging area, L2-coherent loads: L1 may still hold the
+            // lines of two sweeps ago), once their epoch is there
+            const bool need_l = it.c0 < SWEEP_HALO, need_r = it.c0 + T::LC + SWEEP_HALO > nx;
+            if (need_l || need_r) {
+                if (lane == 0) {
+                    if (need_l) wait_epoch(a.flags, 0, a.wait_epoch);
+                    if (need_r) wait_epoch(a.flags, 1, a.wait_epoch);
+                }
+                __syncwarp();
+                const int side = lane / 12, e = lane - 12 * side, v = e / 3, j = e - 3 * v;  // lanes 0-11: left, 12-23: right
+                if (lane < 24 && (side == 0 ? need_l : need_r)) {
+                    const double2* st = reinterpret_cast<const double2*>(halo_stage(a.flags, nz, a.wait_epoch, side)) +
+                                        ((size_t)v * nz + it.k) * 3 + j;
+                    double2 h;
+                    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(h.x), "=d"(h.y) : "l"(st) : "memory");
+                    const int tcol = (side == 0 ? 0 : nx - it.c0 + SWEEP_HALO) + 2 * j;  // tile column of the halo pair
+                    *reinterpret_cast<double2*>(sS + buf * T::S_ELEMS + v * FW + tcol) = h;
+                }
+                __syncwarp();
+            }
+        }
         IfaceBg bg;
         {
             const double2 b01 = *reinterpret_cast<const double2*>(sBg + 4 * buf), b23 = *reinterpret_cast<const double2*>(sBg + 4 * buf + 2);
