@@ -74,3 +74,26 @@ def test_gravity_source_restatement_matches_reference():
         ref.evolve(1)
         no.evolve(case)
     assert np.array_equal(ref.fields.state, case.state)
+
+
+def test_ref_copy_is_verbatim_and_git_ignored():
+    """oracle/_ref (made by oracle/make_ref.py) is what the GPU box uses as THE reference: byte for byte the mounted
+    package, and never part of the history."""
+    import filecmp
+    from oracle import make_ref
+    mount = os.path.join(os.environ.get("PMW_REFERENCE_ROOT", "/root/reference"), "pyminiweather")
+    if not os.path.isdir(mount):
+        pytest.skip("no mounted reference to compare the copy with")
+    dst = make_ref.make()
+    assert dst and os.path.isdir(os.path.join(dst, "pyminiweather"))
+
+    def walk(cmp):
+        assert not cmp.left_only and not cmp.diff_files, (cmp.left_only, cmp.diff_files)
+        for sub in cmp.subdirs.values():
+            walk(sub)
+    walk(filecmp.dircmp(mount, os.path.join(dst, "pyminiweather"), ignore=["__pycache__"]))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["git", "-C", root, "check-ignore", "oracle/_ref/pyminiweather/__init__.py"], capture_output=True, text=True)
+    assert out.returncode == 0, "oracle/_ref must be listed in .gitignore"
+    ignore = os.path.join(root, ".gpurunignore")
+    assert not os.path.exists(ignore) or "oracle/_ref" not in open(ignore).read()
