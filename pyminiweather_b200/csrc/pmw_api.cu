@@ -208,7 +208,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->push_all_cells = 0;  // never (measured worse: every CTA then waits for its peer stores, profiles/r2ae)
     c->dyn_items = 1;  // x sweeps of a slab ring draw their items from a counter (0 never, 2 always)
     c->sweep_z3 = 0;  // z sweeps: 1 = stage-pipelined CTA of three warps (pmw_zpipe.cuh), 0 = one warp per strip (sweep_z)
-    c->sweep_zt = 0;  // z sweeps: 0 = streaming kernel (72 us at 2048x1024), 1 = transposing x-style kernel (90 us)
+    c->sweep_zt = -1;  // z sweeps: 0 = streaming kernel, 1 = transposing x-style kernel, -1 = by grid size (kZtMaxCells)
     c->l2p[PMW_BUF_STATE] = 0;
     c->l2p[PMW_BUF_TMP] = 1;
     c->spare = 2;
@@ -348,7 +348,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
         NEED(value == 0 || value >= 8, "sweep_lz must be 0 (automatic) or >= 8");
         c->sweep_lz = value;
     } else if (!strcmp(key, "sweep_zt")) {
-        c->sweep_zt = value ? 1 : 0;
+        NEED(value >= -1 && value <= 1, "sweep_zt must be -1 (by grid size), 0 (streaming) or 1 (transposing)");
+        c->sweep_zt = value;
     } else if (!strcmp(key, "sweep_z3")) {
         c->sweep_z3 = value ? 1 : 0;
     } else if (!strcmp(key, "sweep_xp")) {
@@ -1136,6 +1137,16 @@ static int pick_sweep_lz(const pmw_ctx* c, int units_per_sm = kZWarpsPerSM, doub
     return best_lz;
 }
 
+// Which z sweep a grid gets.  The streaming kernel (sweep_z) cannot be shorter than one warp's chain of ~(8 + 26)
+// iterations, ~20 us, however small the grid; the transposing kernel (sweep_zt) has no such floor but costs 1.6 x as
+// much per cell once the GPU is full.  They cross at ~0.5 M cells (profiles/r2ak, r2al: 100x50 7.0 vs 19.8 us,
+// 512x256 11.9 vs 23.1, 1024x512 29.2 vs 28.7, 2048x1024 90.8 vs 57.8).
+static const long long kZtMaxCells = 400000;
+static bool use_zt(const pmw_ctx* c)
+{
+    return c->sweep_zt == 1 || (c->sweep_zt < 0 && (long long)c->p.nx * c->p.nz <= kZtMaxCells);
+}
+
 static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool write_tmp, double dt)
 {
     trim_tmaps(c);
@@ -1247,7 +1258,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
 #undef GO
 #undef GO_S
         LAUNCHED(c, "sweep_x");
-    } else if (c->sweep_zt && !has_src) {
+    } else if (use_zt(c) && !has_src) {
         // transposing z sweep: items = (group of 4 columns, z tile); as many CTAs as are resident at once
         const int P = 2, LC = 64 * P - 10;
         if ((rc = get_tmap(c, pS, 4, 64 * P + 4, &tm, true)) != PMW_OK) return rc;

@@ -102,18 +102,24 @@ class Fields:
             self._solver.reverse_direction = reverse
             self._solver_key = key
             self._source_ic = None
+            self._hydro_digest = None
             self._host_dirty = {PMW_BUF_STATE: True, PMW_BUF_TMP: True}
-        hydro = [getattr(self, n) for n in HYDRO_NAMES]
-        # profiles still all-zero (init() not run yet): leave them unset -- operators that need them
-        # then fail with "hydrostatic profiles not set", the pure stencil shims work regardless
-        if all(np.all(h > 0) for h in hydro[:4]) and not self._solver.hydro_matches(hydro):
-            self._solver.set_hydrostatic(*hydro)
+        # The 1-D profiles and the configuration are re-validated on every call (the caller owns those arrays and may
+        # change them), but cheaply: one byte string of the five profiles against the one seen last -- nine small NumPy
+        # calls here made a 100x50 step host-bound (24 us per call for 12 us of kernels).
+        digest = b"".join([getattr(self, n).tobytes() for n in HYDRO_NAMES])
         ic = params.get("ic_type")
-        if ic != self.__dict__.get("_source_ic"):  # the forcing field only depends on the configuration
-            from .._dispatch import sync_inflow, sync_source
+        if digest != self.__dict__.get("_hydro_digest") or ic != self.__dict__.get("_source_ic"):
+            hydro = [getattr(self, n) for n in HYDRO_NAMES]
+            # profiles still all-zero (init() not run yet): leave them unset -- operators that need them
+            # then fail with "hydrostatic profiles not set", the pure stencil shims work regardless
+            if all(np.all(h > 0) for h in hydro[:4]) and not self._solver.hydro_matches(hydro):
+                self._solver.set_hydrostatic(*hydro)
+            from .._dispatch import sync_inflow, sync_source  # the forcing field only depends on the configuration
             sync_source(self._solver, params, self.hy_dens_cell)
             sync_inflow(self._solver, params, ic)
             self._source_ic = ic if np.all(self.hy_dens_cell > 0) else None
+            self._hydro_digest = digest if self._source_ic is not None else None
         for buf in (PMW_BUF_STATE, PMW_BUF_TMP):
             if self._host_dirty[buf]:
                 self._solver.upload(buf, self._host[buf])

@@ -236,7 +236,7 @@ def test_pow_fallback_branch_large_perturbation():
         s.close()
 
 
-@pytest.mark.parametrize("zsweep", [dict(sweep_zt=1), dict(), dict(sweep_z3=1)], ids=["z-transposing", "z-streaming", "z-pipelined"])
+@pytest.mark.parametrize("zsweep", [dict(sweep_zt=1), dict(sweep_zt=0), dict(sweep_zt=0, sweep_z3=1)], ids=["z-transposing", "z-streaming", "z-pipelined"])
 def test_fused_sweeps_pow_fallback_is_bitwise_the_staged_path(zsweep):
     """|eps| > 1/8 inside the FUSED sweeps: a patch of the domain carries 20 % rho*theta perturbations, so
     some warps leave the polynomial (cold call in the x and streaming z sweeps, bail-out to the generic
@@ -426,7 +426,7 @@ def test_chunked_sweeps_are_bitwise_identical(chunks):
     (236, 40, 2, dict(sweep_lz=8)),                # nx = 2 full x tiles exactly (rem == tile)
     (238, 40, 2, dict(sweep_lz=13)),               # ... plus a 2-cell remainder tile
 ])
-@pytest.mark.parametrize("zsweep", [dict(sweep_zt=1), dict(), dict(sweep_z3=1)], ids=["z-transposing", "z-streaming", "z-pipelined"])
+@pytest.mark.parametrize("zsweep", [dict(sweep_zt=1), dict(sweep_zt=0), dict(sweep_zt=0, sweep_z3=1)], ids=["z-transposing", "z-streaming", "z-pipelined"])
 def test_fused_sweeps_bitwise_equal_stage_by_stage(nx, nz, steps, tune, pow_mode, zsweep):
     """One kernel per directional sweep (T1, T2 on chip, 6-cell halo recomputed) against one kernel
     per RK stage: identical bits for the state (interior and x halo images) and for state_tmp -- for every

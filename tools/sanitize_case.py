@@ -28,7 +28,7 @@ for variant in ("tma", "direct"):
         if variant == "tma":  # the other sweep organisations: transposing z sweep, stage-by-stage kernels
             _, c2 = new_case(nx, nz, "collision")
             no.evolve(c2); no.evolve(c2); no.evolve(c2)
-            for tune in (dict(fuse=1, sweep_zt=1), dict(fuse=1, sweep_zt=0, sweep_lz=9), dict(fuse=1, sweep_z3=1, sweep_lz=9),
+            for tune in (dict(fuse=1, sweep_zt=1), dict(fuse=1, sweep_zt=0, sweep_lz=9), dict(fuse=1, sweep_zt=0, sweep_z3=1, sweep_lz=9),
                          dict(fuse=0)):
                 t = DeviceSolver(nx, nz, case.dx, case.dz, case.dt, variant=variant)
                 t.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); t.set_tuning(**tune)
@@ -44,7 +44,7 @@ for variant in ("tma", "direct"):
 # kernel on an odd width, the FP64 probe
 from helpers import synthetic_case
 p, case = new_case(130, 33, "gravity")
-for tune in (dict(fuse=1, sweep_lz=9), dict(fuse=1, sweep_z3=1, sweep_lz=9)):
+for tune in (dict(fuse=1, sweep_zt=0, sweep_lz=9), dict(fuse=1, sweep_zt=0, sweep_z3=1, sweep_lz=9)):
     s = DeviceSolver(130, 33, case.dx, case.dz, case.dt)
     s.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); s.set_tuning(**tune); s.set_source_w(case.source_w)
     s.upload(0, case.state); s.upload(1, case.state_tmp); s.evolve(3); print("gravity", tune, s.stats(0), flush=True); s.close()
@@ -62,7 +62,7 @@ for ic in ("injection", "collision"):
 p, case = synthetic_case(150, 40, seed=5)
 case.state[3, 10:25, 20:90] += 0.2 * case.hy_dens_theta_cell[10:25, None]
 case.state_tmp[:] = case.state
-for tune in (dict(fuse=1, sweep_lz=16), dict(fuse=1, sweep_z3=1, sweep_lz=16), dict(fuse=1, sweep_zt=1)):
+for tune in (dict(fuse=1, sweep_zt=0, sweep_lz=16), dict(fuse=1, sweep_zt=0, sweep_z3=1, sweep_lz=16), dict(fuse=1, sweep_zt=1)):
     s = DeviceSolver(150, 40, case.dx, case.dz, case.dt)
     s.set_hydrostatic(*[getattr(case, n) for n in HYDRO]); s.set_tuning(**tune)
     s.upload(0, case.state); s.upload(1, case.state_tmp); s.evolve(2); print("pow fallback", tune, s.stats(0), flush=True); s.close()
