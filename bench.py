@@ -84,7 +84,7 @@ def make_params(nx_local, nz, world, ic_type="thermal", dx=None):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.power = [], set(), []
