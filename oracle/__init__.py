@@ -13,9 +13,12 @@ Contents
                   is mounted and by the fixtures under ``tests/golden/`` always).
 ``c/``            plain-C (OpenMP) restatement of the same path, used for
                   mid-size parity runs and as the multi-threaded CPU baseline.
-``reference_runner``  helpers that import the *real* reference from
-                  ``/root/reference`` (only inside the build container) to
-                  validate the restatements and generate golden vectors.
+``reference_runner``  helpers that import the *real* reference -- from
+                  ``/root/reference`` in the build container, else from the
+                  verbatim copy ``oracle/_ref`` -- to validate the restatements,
+                  generate golden vectors and time the CPU baseline.
+``make_ref``      the recipe for ``oracle/_ref`` (git-ignored copy of the
+                  reference package; travels to the GPU box with the snapshot).
 
 Parity status: PINNED -- see ``tests/golden/README.md``.
 """

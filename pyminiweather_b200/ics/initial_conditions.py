@@ -3,7 +3,7 @@
 Each ``--ic-type`` is a hydrostatic background (constant potential temperature, or constant
 Brunt-Vaisala frequency for ``gravity``) plus a list of potential-temperature bubbles and a
 uniform wind.  Host NumPy, init-time only; the arithmetic follows the reference expression
-by expression so that the generated fields are bit-identical (tests/test_init_parity.py).
+by expression so that the generated fields are bit-identical (tests/test_reference_style.py against the ic_*_32x16 fixtures).
 """
 from __future__ import annotations
 

@@ -43,7 +43,7 @@ def case_from_golden(g, state_key="state0", tmp_key=None, ic_type="thermal"):
 
 
 def new_case(nx, nz, ic_type="thermal", **kw):
-    """Initial condition from OUR init (bit-identical to the reference's, tests/test_init_parity.py)."""
+    """Initial condition from OUR init (bit-identical to the reference's: tests/test_reference_style.py against the ic_*_32x16 fixtures)."""
     from pyminiweather_b200.data import initialize_fields
     from pyminiweather_b200.ics import init
     from pyminiweather_b200.mesh import MeshData
