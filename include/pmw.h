@@ -157,6 +157,17 @@ int pmw_discrete_step(pmw_ctx *ctx, int direction, int init_buf, int forcing_buf
  * inflow rows (pmw_set_inflow: x is not periodic) runs the reference's own sequence instead --
  * halo-fill kernel, then fused stage kernel, per stage (pmw_discrete_step x 6 per step). */
 int pmw_evolve(pmw_ctx *ctx, int nsteps, double dt);
+/* One evolve (pyminiweather/solve/step.py:85-143) on a HOST array -- what the reference's driver does when
+ * `fields.state` is a NumPy array (pyminiweather/__main__.py:237): host_state is the dense
+ * [4][nz+4][nx+4] array, updated in place.  Same result as pmw_upload_state + pmw_evolve(1) +
+ * pmw_download_state (bit for bit), but streamed in `nbands` bands of rows (0 = chosen from the grid): a
+ * step only couples rows through the 6-row halo of the z sweep, so the upload of later bands, the two fused
+ * sweeps of a band and the download of earlier bands overlap, and the call costs about ONE transfer of
+ * the state over PCIe instead of two.  The reference's state_tmp is not produced (the tmp buffer holds
+ * the previous state afterwards).  Contexts the banded path does not cover (slab rings, inflow rows,
+ * gravity-wave forcing, grids run by the transposing z sweep, "fuse" off) take the plain sequence.
+ * Pinned host memory gives the overlap; pageable memory works, more slowly. */
+int pmw_evolve_host(pmw_ctx *ctx, double *host_state, double dt, int nbands);
 /* One RK stage (rk_stage = 1,2,3) of the fused step on the context's rotating buffers, for
  * callers that interleave their own work between stages (slab halo exchange).  The caller
  * sequences directions/stages as evolve does and flips the direction flag itself. */

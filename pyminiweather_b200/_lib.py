@@ -70,6 +70,7 @@ SIGNATURES = {
     "pmw_stage": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "pmw_discrete_step": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "pmw_evolve": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "pmw_evolve_host": (C.c_int, [_vp, _vp, C.c_double, C.c_int]),
     "pmw_evolve_stage": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double]),
     "pmw_get_reverse_direction": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "pmw_set_reverse_direction": (C.c_int, [_vp, C.c_int]),

@@ -116,6 +116,10 @@ struct pmw_ctx {
     cudaEvent_t ev_fork, ev_join[4];
     cudaStream_t launch_stream;  // stream the stage launch helpers use
     int cur_chunk, cur_nchunks;
+    // pmw_evolve_host: copy streams (H2D, D2H) and one event per band and direction
+    cudaStream_t hs_stream[2];
+    std::vector<cudaEvent_t> hs_ev;
+    cudaEvent_t hs_start;
     // bookkeeping
     long long launches;
     bool timing;
@@ -184,6 +188,8 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->chunks = ((long long)params->nx * params->nz >= (1ll << 20)) ? 2 : 1;
     for (int k = 0; k < 4; ++k) { c->cstream[k] = nullptr; c->ev_join[k] = nullptr; }
     c->ev_fork = nullptr;
+    c->hs_stream[0] = c->hs_stream[1] = nullptr;
+    c->hs_start = nullptr;
     c->launch_stream = nullptr;
     c->cur_chunk = 0;
     c->cur_nchunks = 1;
@@ -276,6 +282,10 @@ extern "C" int pmw_destroy(pmw_ctx* c)
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int k = 0; k < 2; ++k)
+        if (c->hs_stream[k]) { cudaStreamSynchronize(c->hs_stream[k]); cudaStreamDestroy(c->hs_stream[k]); }
+    for (cudaEvent_t e : c->hs_ev) cudaEventDestroy(e);
+    if (c->hs_start) cudaEventDestroy(c->hs_start);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->flags) cudaFree(c->flags);
     if (c->edge_counters) cudaFree(c->edge_counters);
@@ -1114,18 +1124,20 @@ static bool fuse_ok(const pmw_ctx* c)
 static const int kZWarpsPerSM = PMW_ZSWEEP_MINB;
 // `units_per_sm` resident work units (warps of sweep_z, CTAs of sweep_z3) per SM; a unit costs
 // `stages * lz + fill` interface evaluations.
-static int pick_sweep_lz(const pmw_ctx* c, int units_per_sm = kZWarpsPerSM, double stages = 3.0, double fill = 26.0)
+static int pick_sweep_lz(const pmw_ctx* c, int units_per_sm = kZWarpsPerSM, double stages = 3.0, double fill = 26.0,
+                         int nrows = 0)
 {
-    if (c->sweep_lz) return std::min(c->sweep_lz, c->p.nz);
+    if (nrows <= 0) nrows = c->p.nz;  // rows of this launch (a band of pmw_evolve_host, else the whole grid)
+    if (c->sweep_lz) return std::min(c->sweep_lz, nrows);
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
     const long long strips = (c->p.nx + ZS_COLS - 1) / ZS_COLS;
     const long long slots = (long long)nsm * units_per_sm;
     double best = 1e300;
-    int best_lz = c->p.nz;
-    for (int nseg = 1; nseg <= c->p.nz / 8; ++nseg) {
-        const int lz = (c->p.nz + nseg - 1) / nseg;
-        if ((c->p.nz + lz - 1) / lz != nseg) continue;
+    int best_lz = nrows;
+    for (int nseg = 1; nseg <= std::max(nrows / 8, 1); ++nseg) {
+        const int lz = (nrows + nseg - 1) / nseg;
+        if ((nrows + lz - 1) / lz != nseg) continue;
         const long long warps = strips * nseg;
         const long long waves = (warps + slots - 1) / slots;
         // time ~ waves x (work of one unit, with the recomputed rows) x (how full the SMs are)
@@ -1147,8 +1159,13 @@ static bool use_zt(const pmw_ctx* c)
     return c->sweep_zt == 1 || (c->sweep_zt < 0 && (long long)c->p.nx * c->p.nz <= kZtMaxCells);
 }
 
-static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool write_tmp, double dt)
+// row0, row1: the interior rows the launch produces (SweepArgs::row0/row1; row1 < 0: the whole grid)
+static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool write_tmp, double dt, int row0 = 0,
+                        int row1 = -1)
 {
+    if (row1 < 0) row1 = c->p.nz;
+    const bool whole = row0 == 0 && row1 == c->p.nz;
+    NEED(row0 >= 0 && row0 < row1 && row1 <= c->p.nz, "sweep: bad row range");
     trim_tmaps(c);
     NEED(c->hydro_set, "sweep: hydrostatic profiles not set (pmw_set_hydrostatic)");
     SweepArgs a;
@@ -1169,6 +1186,8 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     a.periodic = c->p.periodic_x ? 1 : 0;
     a.lz = 0;
     a.tile_x0 = a.tile_y0 = 0;
+    a.row0 = row0;
+    a.row1 = row1;
     a.flags = c->flags;
     a.wait_epoch = a.push_epoch = 0;
     a.edge_last = 0;
@@ -1193,6 +1212,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     }
     if (direction == PMW_DIR_X) {
         if (c->peers) {
+            NEED(whole, "sweep: row bands are single-context only");
             a.push_epoch = a.wait_epoch = ++c->epoch;
             a.edge_last = 1;
             a.nbr_state_left = c->nbr_base[0][pS];
@@ -1201,10 +1221,12 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
             a.nbr_flags_right = c->nbr_flags[1];
         } else if (!c->xhalo6_valid[pS]) {
             NEED(c->p.periodic_x, "pmw_evolve: the x halo of the state is stale on a slab context without peers");
-            const int n = NVAR * c->p.nz * 6;
-            bc_x6_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[pS], c->L);
+            Layout Lb = c->L;  // the rows of this launch only (idx() never uses nz: the offset pointer does it)
+            Lb.nz = row1 - row0;
+            const int n = NVAR * Lb.nz * 6;
+            bc_x6_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->base[pS] + (long long)row0 * c->L.pitch, Lb);
             LAUNCHED(c, "bc_x6_kernel");
-            c->xhalo_valid[pS] = c->xhalo6_valid[pS] = true;
+            if (whole) c->xhalo_valid[pS] = c->xhalo6_valid[pS] = true;
         }
         const int P = c->sweep_xp;
         const int LC = 64 * P - 10;
@@ -1214,7 +1236,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->p.device);
         // persistent: every warp walks its own list of (row, tile) items; as many CTAs of 4 warps as
         // are resident at once
-        const long long nitems = (long long)c->p.nz * ntx;
+        const long long nitems = (long long)(row1 - row0) * ntx;
         // "dyn_items": 0 never, 1 slab ring, 2 always (not with the gravity-wave forcing: single slab only)
         const bool dyn_items = !has_src && (c->peers ? (c->dyn_items != 0) : (c->dyn_items == 2));
         if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
@@ -1259,6 +1281,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
 #undef GO_S
         LAUNCHED(c, "sweep_x");
     } else if (use_zt(c) && !has_src) {
+        NEED(whole, "sweep: row bands need the streaming z sweep");
         // transposing z sweep: items = (group of 4 columns, z tile); as many CTAs as are resident at once
         const int P = 2, LC = 64 * P - 10;
         if ((rc = get_tmap(c, pS, 4, 64 * P + 4, &tm, true)) != PMW_OK) return rc;
@@ -1289,6 +1312,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
 #undef GO
         LAUNCHED(c, "sweep_zt");
     } else if (c->sweep_z3) {
+        NEED(whole, "sweep: row bands need the streaming z sweep");
         // stage-pipelined z sweep: CTA = 3 warps = the three stages of one strip segment
         if ((rc = get_tmap(c, pS, Z3_COLS, 4, &tm, true)) != PMW_OK) return rc;
 #define GO_S(PM, WT, SRC)                                                                                  \
@@ -1316,12 +1340,21 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
 #undef GO_S
         LAUNCHED(c, "sweep_z3");
     } else {
-        a.lz = pick_sweep_lz(c);
+        a.lz = pick_sweep_lz(c, kZWarpsPerSM, 3.0, 26.0, row1 - row0);
         if ((rc = get_tmap(c, pS, ZS_COLS, 1, &tm, true)) != PMW_OK) return rc;
-        const dim3 grid((c->p.nx + ZS_COLS - 1) / ZS_COLS, (c->p.nz + a.lz - 1) / a.lz);
+        const dim3 grid((c->p.nx + ZS_COLS - 1) / ZS_COLS, (row1 - row0 + a.lz - 1) / a.lz);
         if (e0) CU_TRY(cudaEventRecord(e0, c->stream));
-#define GO_S(PM, WT, SRC) \
-    launch_ex(sweep_z<PM, WT, SRC>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl && !c->timing, *tm, a)
+#define GO_S(PM, WT, SRC)                                                                                        \
+    do {                                                                                                         \
+        static unsigned long long attr_done = 0; /* one bit per device: all of the SM's shared memory, so that */ \
+        if (!(attr_done >> c->p.device & 1ull)) { /* kZWarpsPerSM one-warp CTAs fit */                            \
+            CU_TRY(cudaFuncSetAttribute(sweep_z<PM, WT, SRC>, cudaFuncAttributePreferredSharedMemoryCarveout,    \
+                                        cudaSharedmemCarveoutMaxShared));                                        \
+            attr_done |= 1ull << c->p.device;                                                                    \
+        }                                                                                                        \
+        launch_ex(sweep_z<PM, WT, SRC>, grid, dim3(32), zsweep_smem_bytes(), c->stream, c->pdl && !c->timing,    \
+                  *tm, a);                                                                                       \
+    } while (0)
 #define GO(PM, WT) do { if (has_src) GO_S(PM, WT, true); else GO_S(PM, WT, false); } while (0)
         if (fast) { if (write_tmp) GO(1, true); else GO(1, false); }
         else      { if (write_tmp) GO(0, true); else GO(0, false); }
@@ -1332,7 +1365,7 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     if (e1) CU_TRY(cudaEventRecord(e1, c->stream));
     // S' carries the periodic images of its own edge columns (single slab); in a ring they are pushed
     // by the next x sweep
-    c->xhalo_valid[pO] = c->xhalo6_valid[pO] = (c->p.periodic_x != 0);
+    if (whole) c->xhalo_valid[pO] = c->xhalo6_valid[pO] = (c->p.periodic_x != 0);
     return PMW_OK;
 }
 
@@ -1397,6 +1430,113 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
         }
         c->reverse = !c->reverse;
     }
+    return PMW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One time step on a HOST array, streamed in row bands
+// ---------------------------------------------------------------------------------------------
+// What the drop-in `evolve` on host arrays costs is PCIe: 2 x 67.5 MB at 2048 x 1024 against 0.1 ms of
+// kernels, and upload -> step -> download one after the other uses one direction of the link at a time.
+// But a step only couples rows through the z sweep's 6-row halo (three stages x two cells), and the x sweep
+// not at all: the final rows [k0, k1) depend on the initial rows [k0-6, k1+6) alone.  So the step runs in
+// bands of rows -- band b is uploaded on one copy stream, swept (both directions, row-range launches of the
+// same fused kernels: bit-identical to the whole-grid launches) on the context's stream as soon as band b+1
+// has arrived, and downloaded on a second copy stream while later bands are still on their way up: H2D and
+// D2H overlap and the call takes little more than ONE transfer of the state.  Buffers: the upload goes to the
+// state buffer A, the first sweep writes the spare buffer C, the second the tmp buffer B (A cannot take it:
+// later bands still read A's rows next to the band), B becomes the state.  The reference's state_tmp is
+// not produced (it is scratch there, solve/step.py:112-141).  The host array is updated in place: a band's
+// download only overwrites rows whose upload has completed.
+static int evolve_host_plain(pmw_ctx* c, double* host, double dt)
+{
+    int rc = copy_state(c, PMW_BUF_STATE, host, true, false);
+    if (rc == PMW_OK) rc = pmw_evolve(c, 1, dt);
+    if (rc == PMW_OK) rc = copy_state(c, PMW_BUF_STATE, host, false, true);
+    return rc != PMW_OK ? rc : check_watchdog(c);
+}
+
+extern "C" int pmw_evolve_host(pmw_ctx* c, double* host_state, double dt, int nbands)
+{
+    BIND(c);
+    NEED(host_state, "pmw_evolve_host: null host pointer");
+    NEED(nbands >= 0, "pmw_evolve_host: negative band count");
+    if (dt <= 0) dt = c->p.dt;
+    const int nz = c->p.nz;
+    const bool can_band = fuse_ok(c) && c->p.periodic_x && !c->peers && !c->jet_rows && !c->src_w && !use_zt(c) &&
+                          !c->sweep_z3 && !c->timing;
+    if (nbands == 0)  // bands of ~64 rows (a 16 KB row at nx = 2048: ~1 MB per band and variable), 32 at most
+        nbands = std::min(32, nz / 64);
+    nbands = std::min(nbands, nz / 16);
+    if (!can_band || nbands < 2) return evolve_host_plain(c, host_state, dt);
+
+    for (int k = 0; k < 2; ++k)
+        if (!c->hs_stream[k]) CU_TRY(cudaStreamCreateWithFlags(&c->hs_stream[k], cudaStreamNonBlocking));
+    if (!c->hs_start) CU_TRY(cudaEventCreateWithFlags(&c->hs_start, cudaEventDisableTiming));
+    while ((int)c->hs_ev.size() < 2 * nbands) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->hs_ev.push_back(e);
+    }
+    cudaStream_t up = c->hs_stream[0], down = c->hs_stream[1];
+    const int A = c->l2p[PMW_BUF_STATE], B = c->l2p[PMW_BUF_TMP], C = c->spare;
+    const bool xfirst = c->reverse != 0;
+    const size_t NX = c->p.nx + 4;
+    // one 3-D copy per band and direction: [4 variables][rows of the band][nx+4]
+    auto copy_band = [&](int buf, int ar0, int ar1, bool to_device, cudaStream_t st) -> cudaError_t {
+        cudaMemcpy3DParms q = {};
+        const cudaPitchedPtr h = make_cudaPitchedPtr(host_state, NX * sizeof(double), NX * sizeof(double), nz + 4);
+        const cudaPitchedPtr d = make_cudaPitchedPtr(c->base[buf], c->L.pitch * sizeof(double), NX * sizeof(double), nz + 4);
+        q.srcPtr = to_device ? h : d;
+        q.dstPtr = to_device ? d : h;
+        q.srcPos = q.dstPos = make_cudaPos(0, ar0, 0);
+        q.extent = make_cudaExtent(NX * sizeof(double), ar1 - ar0, NVAR);
+        q.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        return cudaMemcpy3DAsync(&q, st);
+    };
+    auto k_lo = [&](int b) { return (int)((long long)nz * b / nbands); };          // first interior row of band b
+    auto a_lo = [&](int b) { return b == 0 ? 0 : k_lo(b) + HS; };                   // ... array row (band 0: + halo rows)
+    auto a_hi = [&](int b) { return b == nbands - 1 ? nz + 2 * HS : k_lo(b + 1) + HS; };
+
+    // earlier work of the context (kernels reading or writing the three buffers) before the first upload lands
+    CU_TRY(cudaEventRecord(c->hs_start, c->stream));
+    CU_TRY(cudaStreamWaitEvent(up, c->hs_start, 0));
+    CU_TRY(cudaStreamWaitEvent(down, c->hs_start, 0));
+    for (int b = 0; b < nbands; ++b) {
+        CU_TRY(copy_band(A, a_lo(b), a_hi(b), true, up));
+        CU_TRY(cudaEventRecord(c->hs_ev[b], up));
+    }
+    c->xhalo_valid[A] = c->xhalo6_valid[A] = false;  // every band's x sweep fills the 6-wide wrap of its rows
+    int xdone = 0, rc = PMW_OK;
+    for (int b = 0; b < nbands && rc == PMW_OK; ++b) {
+        const int k0 = k_lo(b), k1 = k_lo(b + 1);
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->hs_ev[std::min(b + 1, nbands - 1)], 0));  // rows up to k1 + 6
+        if (!xfirst) {
+            rc = launch_sweep(c, PMW_DIR_Z, A, C, B, false, dt, k0, k1);
+            c->xhalo_valid[C] = c->xhalo6_valid[C] = true;  // the z sweep stored the periodic images of its rows
+            if (rc == PMW_OK) rc = launch_sweep(c, PMW_DIR_X, C, B, B, false, dt, k0, k1);
+        } else {
+            const int xe = (b == nbands - 1) ? nz : std::min(k1 + SWEEP_HALO, nz);  // the z sweep reads six rows beyond the band
+            if (xe > xdone) rc = launch_sweep(c, PMW_DIR_X, A, C, B, false, dt, xdone, xe);
+            xdone = std::max(xdone, xe);
+            if (rc == PMW_OK) rc = launch_sweep(c, PMW_DIR_Z, C, B, B, false, dt, k0, k1);
+        }
+        if (rc != PMW_OK) break;
+        CU_TRY(cudaEventRecord(c->hs_ev[nbands + b], c->stream));
+        CU_TRY(cudaStreamWaitEvent(down, c->hs_ev[nbands + b], 0));
+        CU_TRY(copy_band(B, a_lo(b), a_hi(b), false, down));
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(down), e2 = cudaStreamSynchronize(up), e3 = cudaStreamSynchronize(c->stream);
+    if (rc != PMW_OK) return rc;
+    CU_TRY(e1);
+    CU_TRY(e2);
+    CU_TRY(e3);
+    c->l2p[PMW_BUF_STATE] = B;  // the new state, with the periodic images of its edge columns
+    c->l2p[PMW_BUF_TMP] = A;    // (holds the previous state, not the reference's stage-2 array)
+    c->spare = C;
+    c->xhalo_valid[B] = c->xhalo6_valid[B] = true;
+    c->xhalo_valid[C] = c->xhalo6_valid[C] = false;
+    c->reverse = !c->reverse;
     return PMW_OK;
 }
 

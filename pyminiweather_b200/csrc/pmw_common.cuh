@@ -190,20 +190,21 @@ __device__ __forceinline__ double pow1p_gamma_m1(double e)
     return fma(b, e, a) * e;
 }
 
-// 1/x for normal, positive x (densities): MUFU.RCP64H seed (>= 20 good bits) and Newton steps.
-// Straight-line code -- __drcp_rn carries a branch for special operands, which splits the basic
-// block of every interface evaluation and keeps the scheduler from interleaving independent
-// evaluations.  The seed is good to 2^-19.9, so two steps reach 2^-80 before the final rounding:
-// correctly rounded on all 2e8 samples of tools/arith_probe/rcp_probe.cu.
+// 1/x for normal, positive x (densities): MUFU.RCP64H seed and ONE cubically convergent step,
+//     r = r0 (1 + e + e^2),  e = 1 - x r0:
+// the seed is good to 2^-19.9 (tools/arith_probe/rcp_probe.cu), so the result is good to 2^-59.7 before
+// its final rounding -- within 0.51 ulp of 1/x.  Straight-line code: __drcp_rn carries a branch for special
+// operands, which splits the basic block of every interface evaluation and keeps the scheduler from
+// interleaving independent evaluations.  (Two Newton steps -- four dependent FMAs, correctly rounded on all
+// 2e8 samples of the probe -- were one FMA more on the longest dependency chain of an interface: the
+// sweeps are 1.6 % faster with the cubic step, profiles/r2ba_ab.log.)
 __device__ __forceinline__ double rcp_pos(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // Everything one interface needs besides the 4x4 stencil values.

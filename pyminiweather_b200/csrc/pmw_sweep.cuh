@@ -70,6 +70,10 @@ struct SweepArgs {
     // start and once per item it processes)
     unsigned long long* item_counter;
     unsigned long long item_base;
+    // interior rows [row0, row1) this launch produces (whole sweep: 0, nz).  A band of rows is what pmw_evolve_host
+    // streams: the sweeps only couple rows through the 6-row halo a z sweep reads from the state, so a band's result
+    // has the bits of the whole sweep's.  (At the end of the struct: the members above keep their alignment.)
+    int row0, row1;
 };
 
 // Slab ring, fused x sweep: where the halo columns travel.  Every context owns a STAGING area behind its flag words
@@ -198,11 +202,11 @@ struct XItem {
 };
 // Items are numbered tile column by tile column (rows fastest); in a slab ring the two edge columns,
 // whose halo cells arrive from the neighbours over NVLink, come last.
-__device__ __forceinline__ XItem xsweep_item(int n, int nz, int ntx, int lc, int edge_last)
+__device__ __forceinline__ XItem xsweep_item(int n, int nrows, int row0, int ntx, int lc, int edge_last)
 {
     XItem it;
-    const int cidx = n / nz;
-    it.k = n - cidx * nz;
+    const int cidx = n / nrows;
+    it.k = row0 + n - cidx * nrows;
     it.tx = !edge_last ? cidx : ((cidx + 2 < ntx) ? cidx + 1 : (cidx + 2 == ntx ? 0 : ntx - 1));
     it.c0 = it.tx * lc;
     return it;
@@ -230,7 +234,8 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     static_assert((T::S_ELEMS * 8) % 128 == 0, "state rows stay 128-byte aligned");
 
     const int nx = a.L.nx, nz = a.L.nz;
-    const int nitems = nz * ntx;
+    const int row0 = a.row0, nrows = a.row1 - a.row0;
+    const int nitems = nrows * ntx;
     const int nwarps = gridDim.x * T::WARPS;
     const int w = blockIdx.x * T::WARPS + warp;
     pdl_launch_dependents();
@@ -284,10 +289,10 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
     };
     unsigned int raw1 = draw();
     int n = min(w, nitems);
-    if (n < nitems && lane == 0) request(xsweep_item(n, nz, ntx, T::LC, a.edge_last), 0);
+    if (n < nitems && lane == 0) request(xsweep_item(n, nrows, row0, ntx, T::LC, a.edge_last), 0);
 #pragma unroll 1
     while (n < nitems) {
-        const XItem it = xsweep_item(n, nz, ntx, T::LC, a.edge_last);
+        const XItem it = xsweep_item(n, nrows, row0, ntx, T::LC, a.edge_last);
         int n_next;
         if (dynamic) {
             n_next = decode(raw1);
@@ -295,7 +300,7 @@ sweep_x(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a, const int
         } else {
             n_next = min(n + nwarps, nitems);
         }
-        if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nz, ntx, T::LC, a.edge_last), buf ^ 1);
+        if (n_next < nitems && lane == 0) request(xsweep_item(n_next, nrows, row0, ntx, T::LC, a.edge_last), buf ^ 1);
         n = n_next;
         // ragged last tile of a row: stage s only needs its output columns t < rem + 12 - 2s, and a pass
         // q only matters while 64q <= that limit (warp-uniform)
@@ -924,7 +929,7 @@ sweep_z(const __grid_constant__ CUtensorMap tm_row, const SweepArgs a)
     const int c0 = (blockIdx.x + a.tile_x0) * ZS_COLS;
     const int i = c0 + lane;
     const bool col_ok = i < nx;
-    const int lo3 = blockIdx.y * a.lz, hi3 = min(lo3 + a.lz, nz);
+    const int lo3 = a.row0 + blockIdx.y * a.lz, hi3 = min(lo3 + a.lz, a.row1);
     const int lo2 = max(lo3 - 2, 0), hi2 = min(hi3 + 2, nz);
     const int lo1 = max(lo3 - 4, 0), hi1 = min(hi3 + 4, nz);
     zs.f0 = lo1 - 2;          // first state cell row of the stream (array row f0 + 2)

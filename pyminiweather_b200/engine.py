@@ -170,6 +170,15 @@ class DeviceSolver:
     def evolve(self, nsteps: int = 1, dt: float | None = None):
         check(self._lib.pmw_evolve(self._h, int(nsteps), float(dt) if dt is not None else -1.0))
 
+    def evolve_host(self, host: np.ndarray, dt: float | None = None, nbands: int = 0):
+        """One ``evolve`` on a host array, in place (``pmw_evolve_host``): upload, the two fused sweeps and
+        download run band by band, so that H2D and D2H overlap.  Same bits as upload + evolve(1) + download."""
+        if not (isinstance(host, np.ndarray) and host.dtype == np.float64 and host.flags.c_contiguous
+                and host.flags.writeable and tuple(host.shape) == self.shape):
+            raise ValueError(f"state must be a writable C-contiguous float64 array of shape {self.shape}")
+        check(self._lib.pmw_evolve_host(self._h, C.c_void_p(host.ctypes.data),
+                                        float(dt) if dt is not None else -1.0, int(nbands)))
+
     def evolve_stage(self, direction: int, rk_stage: int, dt: float | None = None):
         check(self._lib.pmw_evolve_stage(self._h, direction, rk_stage, float(dt) if dt is not None else -1.0))
 

@@ -46,6 +46,8 @@ def _sweep_order(solver):
 # Strict (foreign-fields) mode: also bring state_tmp back after evolve.  It is scratch in
 # the reference; leaving it on the device halves the PCIe traffic of the drop-in call.
 SYNC_STATE_TMP = False
+# Strict mode: row bands of the streamed step (0 = chosen from the grid, 1 = upload, step, download in sequence)
+HOST_BANDS = 0
 
 
 def discrete_step(params, fields, mesh, state_init, state_forcing, state_out, dt, direction) -> None:
@@ -102,6 +104,12 @@ def evolve(params, fields, mesh, dt: float = 1e-4) -> None:
     _sweep_order(solver)
     shape = (4, params["nz"] + 2 * params["hs"], params["nx"] + 2 * params["hs"])
     state = writable_f64(fields.state, shape, "fields.state")
+    if params["ic_type"] != "injection" and not SYNC_STATE_TMP:
+        # the whole call as one band-pipelined pass over PCIe (pmw_evolve_host): upload, sweeps and download
+        # of successive row bands overlap; same bits as the sequence below
+        solver.evolve_host(state, dt, HOST_BANDS)
+        remember_sweep_order(fields, solver)
+        return
     solver.upload(PMW_BUF_STATE, state)
     if params["ic_type"] == "injection":
         # the right halo columns of state_tmp are never refreshed in this configuration (bcs.py:37):

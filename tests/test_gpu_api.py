@@ -396,3 +396,42 @@ def test_sweep_order_belongs_to_the_simulation_and_can_be_reset():
     case.reverse_direction = False; no.evolve(case)
     assert worst_rel_l2(f.state, case.state) <= 1e-11
     f.close()
+
+
+@pytest.mark.parametrize("nx,nz,ic,bands", [(1024, 512, "thermal", 0), (896, 480, "collision", 5), (1024, 416, "thermal", 13),
+                                             (96, 64, "density-current", 4)])
+def test_evolve_host_streams_row_bands_with_the_bits_of_the_plain_sequence(nx, nz, ic, bands):
+    """pmw_evolve_host (the strict drop-in's evolve on host arrays): upload, sweeps and download band by band must
+    give the bits of upload + evolve(1) + download, in both sweep orders (steps alternate Z,X / X,Z), for band
+    counts that do not divide nz, and on grids the banded path does not cover (small ones: plain sequence)."""
+    from pyminiweather_b200._lib import PMW_BUF_STATE
+    from pyminiweather_b200.engine import DeviceSolver
+    _, case = new_case(nx, nz, ic)
+    solvers = []
+    for _ in range(2):
+        s = DeviceSolver(nx, nz, case.dx, case.dz, case.dt)
+        s.set_hydrostatic(*[getattr(case, k) for k in HYDRO])
+        solvers.append(s)
+    plain, banded = solvers
+    a, b = case.state.copy(), case.state.copy()
+    for step in range(4):
+        plain.upload(PMW_BUF_STATE, a); plain.evolve(1); plain.download(PMW_BUF_STATE, out=a)
+        banded.evolve_host(b, None, bands)
+        assert banded.reverse_direction == plain.reverse_direction == bool((step + 1) & 1)
+        assert np.array_equal(interior(a), interior(b)), f"step {step}"
+        # the halo columns are the periodic images the last sweep stored, as after a plain download
+        assert np.array_equal(a[:, 2:-2, :], b[:, 2:-2, :])
+    # the context stays usable for device-resident stepping afterwards
+    plain.evolve(2); banded.evolve(2)
+    assert np.array_equal(interior(plain.download(PMW_BUF_STATE)), interior(banded.download(PMW_BUF_STATE)))
+    plain.close(); banded.close()
+
+
+def test_strict_dropin_uses_the_streamed_step_and_matches_the_oracle():
+    from pyminiweather_b200.solve import evolve
+    p, case = new_case(512, 384, "collision")
+    f = foreign_fields(case)
+    for _ in range(3):
+        evolve(p, f, None, dt=p["dt"])
+        no.evolve(case)
+        assert worst_rel_l2(f.state, case.state) <= 1e-11

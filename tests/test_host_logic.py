@@ -124,6 +124,13 @@ class OracleSolver:
                 self.discrete_step(d, STATE, TMP, STATE, dt / 1)
             self.reverse_direction = not self.reverse_direction
 
+    def evolve_host(self, host, dt=None, nbands=0):
+        # pmw_evolve_host: one upload, one step and one download of the state (streamed in bands on the device)
+        self.upload(STATE, host)
+        self.evolve(1, dt)
+        self.download(STATE, out=host)
+        self.host_steps = getattr(self, "host_steps", 0) + 1
+
     def stats(self, buf=STATE):
         return no.compute_stats(self._case(), self.buf[buf])
 
@@ -203,6 +210,7 @@ def test_strict_dropin_transfers_every_call(fake_device, ic):
     assert len(fake_device.instances) == 1                          # one context, cached per container
     assert dev.uploads.count(STATE) == 3 and dev.downloads.count(STATE) == 3
     assert dev.uploads.count(TMP) == (3 if ic == "injection" else 0)   # state_tmp halos are caller data there
+    assert getattr(dev, "host_steps", 0) == (0 if ic == "injection" else 3)  # the streamed step where it applies
     assert compute_stats(p, ff) == no.compute_stats(case)
     assert np.array_equal(compute_solution_variables(p, ff), no.compute_solution_variables(case))
     # another grid for the same container -> a new context, the old one is closed

@@ -1,6 +1,6 @@
 """A/B timing of libpmw variants (tools/build_variant.py): for every variant, in a fresh process, the
 fused step at nx x nz -- whole, x sweeps only, z sweeps only -- and whether the result still has the
-bits of the stage-by-stage path.   usage: python tools/ab_sweeps.py nx nz steps tag [tag ...]"""
+bits of the stage-by-stage path.   usage: python tools/ab_sweeps.py nx nz steps tag [tag ...] [ic=collision] [key=value ...]"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
@@ -10,8 +10,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     from helpers import new_case, HYDRO
     from pyminiweather_b200.engine import DeviceSolver
     nx, nz, steps = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    extra = {k: int(v) for k, v in (kv.split("=") for kv in sys.argv[5:])}
-    p, case = new_case(nx, nz, "thermal")
+    extra = dict(kv.split("=") for kv in sys.argv[5:])
+    ic = extra.pop("ic", "thermal")  # ic=collision etc.: the initial condition (default thermal)
+    extra = {k: int(v) for k, v in extra.items()}
+    p, case = new_case(nx, nz, ic)
     def run(n, **tune):
         s = DeviceSolver(nx, nz, case.dx, case.dz, case.dt)
         s.set_hydrostatic(*[getattr(case, k) for k in HYDRO]); s.set_tuning(**tune)
