@@ -232,7 +232,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->launches = 0;
     c->timing = false;
     c->ev_used = 0;
-    c->stats_blocks = 148 * 8;
+    c->stats_blocks = 148 * PMW_STATS_MINB;  // persistent: the resident blocks of stats_partial_kernel
     {
         // 8 profile tables + the packed interface table Hydro::int_pack (32-byte aligned, hence the slack)
         const size_t nhy = (size_t)4 * (params->nz + 4) + (size_t)4 * (params->nz + 1) + 4 +

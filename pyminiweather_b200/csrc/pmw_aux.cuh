@@ -140,6 +140,9 @@ __device__ __forceinline__ double warp_sum(double x)
 // K = (cv/C0) (C0/p0)^(R/cp): the two pow() of the reference collapse into the pressure, which is evaluated
 // relative to the row's hydrostatic value exactly as in the flux kernels (pow1p_gamma_m1; pow() itself
 // beyond |e| > 1/8).  Agreement with the two-pow form: ~2e-16 per cell.
+// the rare branch, out of line: pow() inlined costs the diagnostics kernel 40 registers
+__device__ __noinline__ double stats_ie_pow(double dens_theta, double k_c0) { return k_c0 * pow(dens_theta, GAMMA); }
+
 __device__ __forceinline__ double cell_energy(double dens, double mu, double mw, double rt, double hd, double hdt,
                                               double ihdt, double kp_row, double k_c0, double& rho_out)
 {
@@ -148,58 +151,72 @@ __device__ __forceinline__ double cell_energy(double dens, double mu, double mw,
     const double e = rt * ihdt;
     double ie;
     if (fabs(e) <= 0.125) ie = fma(kp_row, pow1p_gamma_m1(e), kp_row);
-    else ie = k_c0 * pow(rt + hdt, GAMMA);
-    return fma(mu, mu, mw * mw) / rho + ie;  // no 1/2 on the kinetic term (stats.py:27)
+    else ie = stats_ie_pow(rt + hdt, k_c0);
+    return fma(fma(mu, mu, mw * mw), rcp_pos(rho), ie);  // no 1/2 on the kinetic term (stats.py:27)
 }
 
-// Pass 1: items = (row, chunk of 1024 columns), grid-stride; 16-byte loads (interior column 0 sits on a
-// 128-byte line, pmw_common.cuh), row constants hoisted, per-thread sums, warp-shuffle tree, one partial per
-// block.  partial[2*b] = sum rho, [2*b+1] = sum(ke+ie).  HBM-bound: 32 B per cell.
-__global__ void __launch_bounds__(256) stats_partial_kernel(const double* __restrict__ s, const Layout L,
-                                                            const double* __restrict__ hd,
-                                                            const double* __restrict__ hdt,
-                                                            const double* __restrict__ ihdt,
-                                                            const double* __restrict__ pcell, const double kconst,
-                                                            double* partial)
+// Pass 1: items = (row, chunk of 512 columns = one 16-byte pair per thread), grid-stride over a persistent grid; the
+// four loads of the NEXT item are in flight while the current one is evaluated; row constants come with them.
+// Per-thread sums, warp-shuffle tree, one partial per block: partial[2*b] = sum rho, [2*b+1] = sum(ke+ie).
+// HBM-bound: 32 B per cell.  (Interior column 0 sits on a 128-byte line, pmw_common.cuh.)
+struct StatsItem {
+    double2 d, u, w, t;
+    int k;  // row, or -1: nothing to do
+};
+#ifndef PMW_STATS_MINB
+#define PMW_STATS_MINB 3  // resident blocks per SM = blocks of the persistent grid per SM (pmw_api.cu: stats_blocks)
+#endif
+__global__ void __launch_bounds__(256, PMW_STATS_MINB) stats_partial_kernel(const double* __restrict__ s, const Layout L,
+                                                               const double* __restrict__ hd,
+                                                               const double* __restrict__ hdt,
+                                                               const double* __restrict__ ihdt,
+                                                               const double* __restrict__ pcell, const double kconst,
+                                                               double* partial)
 {
-    constexpr int CHUNK = 1024;  // columns per item: two double2 per thread and variable, all eight loads in flight
+    constexpr int CHUNK = 512;
     const int nchunks = (L.nx + CHUNK - 1) / CHUNK;
     const int nitems = L.nz * nchunks;
     const double k_c0 = kconst * C0;
     const bool vec = (L.nx & 1) == 0;
     double mass = 0.0, energy = 0.0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int k = item / nchunks, i = (item - k * nchunks) * CHUNK + 2 * threadIdx.x;
-        if (i >= L.nx) continue;
-        const double h = __ldg(hd + k + HS), ht = __ldg(hdt + k + HS), iht = __ldg(ihdt + k + HS);
-        const double kp = kconst * __ldg(pcell + k + HS);
-        const double* p = s + idx(L, 0, k + HS, i + HS);
-        double r0, r1;
-        if (vec) {
-            const bool two = i + CHUNK / 2 < L.nx;  // the thread's second pair, 512 columns further
-            const double* p2 = p + (two ? CHUNK / 2 : 0);
-            const double2 d = *reinterpret_cast<const double2*>(p), d2 = *reinterpret_cast<const double2*>(p2);
-            const double2 u = *reinterpret_cast<const double2*>(p + L.vstride), u2 = *reinterpret_cast<const double2*>(p2 + L.vstride);
-            const double2 w = *reinterpret_cast<const double2*>(p + 2 * L.vstride), w2 = *reinterpret_cast<const double2*>(p2 + 2 * L.vstride);
-            const double2 t = *reinterpret_cast<const double2*>(p + 3 * L.vstride), t2 = *reinterpret_cast<const double2*>(p2 + 3 * L.vstride);
-            energy += cell_energy(d.x, u.x, w.x, t.x, h, ht, iht, kp, k_c0, r0);
-            energy += cell_energy(d.y, u.y, w.y, t.y, h, ht, iht, kp, k_c0, r1);
-            mass += r0 + r1;
-            if (two) {
-                energy += cell_energy(d2.x, u2.x, w2.x, t2.x, h, ht, iht, kp, k_c0, r0);
-                energy += cell_energy(d2.y, u2.y, w2.y, t2.y, h, ht, iht, kp, k_c0, r1);
+    if (vec) {
+        auto fetch = [&](int item) {
+            StatsItem it;
+            const int k = item / nchunks, i = (item - k * nchunks) * CHUNK + 2 * threadIdx.x;
+            it.k = (item < nitems && i < L.nx) ? k : -1;
+            if (it.k >= 0) {
+                const double* p = s + idx(L, 0, k + HS, i + HS);
+                it.d = *reinterpret_cast<const double2*>(p);
+                it.u = *reinterpret_cast<const double2*>(p + L.vstride);
+                it.w = *reinterpret_cast<const double2*>(p + 2 * L.vstride);
+                it.t = *reinterpret_cast<const double2*>(p + 3 * L.vstride);
+            }
+            return it;
+        };
+        StatsItem cur = fetch(blockIdx.x);
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const StatsItem nxt = fetch(item + gridDim.x);
+            if (cur.k >= 0) {
+                // the row's constants: four broadcast loads that hit L1 / L2
+                const double h = __ldg(hd + cur.k + HS), ht = __ldg(hdt + cur.k + HS), iht = __ldg(ihdt + cur.k + HS);
+                const double kp = kconst * __ldg(pcell + cur.k + HS);
+                double r0, r1;
+                energy += cell_energy(cur.d.x, cur.u.x, cur.w.x, cur.t.x, h, ht, iht, kp, k_c0, r0);
+                energy += cell_energy(cur.d.y, cur.u.y, cur.w.y, cur.t.y, h, ht, iht, kp, k_c0, r1);
                 mass += r0 + r1;
             }
-        } else {
-            for (int ii = i; ii < min(i + CHUNK / 2 + 2, L.nx); ii += CHUNK / 2) {
+            cur = nxt;
+        }
+    } else {  // odd widths: one cell per thread and load
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int k = item / nchunks, i0 = (item - k * nchunks) * CHUNK;
+            const double h = __ldg(hd + k + HS), ht = __ldg(hdt + k + HS), iht = __ldg(ihdt + k + HS);
+            const double kp = kconst * __ldg(pcell + k + HS);
+            for (int ii = i0 + threadIdx.x; ii < min(i0 + CHUNK, L.nx); ii += 256) {
                 const double* q = s + idx(L, 0, k + HS, ii + HS);
+                double r0;
                 energy += cell_energy(q[0], q[L.vstride], q[2 * L.vstride], q[3 * L.vstride], h, ht, iht, kp, k_c0, r0);
                 mass += r0;
-                if (ii + 1 < L.nx) {
-                    energy += cell_energy(q[1], q[L.vstride + 1], q[2 * L.vstride + 1], q[3 * L.vstride + 1], h, ht, iht, kp,
-                                          k_c0, r1);
-                    mass += r1;
-                }
             }
         }
     }
