@@ -152,7 +152,7 @@ int pmw_discrete_step(pmw_ctx *ctx, int direction, int init_buf, int forcing_buf
  * Default on the TMA variant: ONE kernel per directional sweep (the three RK stages fused, the
  * two intermediate states on chip, 6-cell halo recomputed; bit-identical to running the stages
  * one by one) -- tuning key "fuse".  The reference's state_tmp (its stage-2 array) is then
- * written by the last sweep of the call only ("keep_tmp").  The gravity-wave forcing
+ * produced by the last sweep of the call only, and by default only when it is asked for ("keep_tmp").  The gravity-wave forcing
  * (pmw_set_source_w) is applied inside the sweeps of a single periodic slab; a context with
  * inflow rows (pmw_set_inflow: x is not periodic) runs the reference's own sequence instead --
  * halo-fill kernel, then fused stage kernel, per stage (pmw_discrete_step x 6 per step). */
@@ -227,7 +227,9 @@ int pmw_peer_status(pmw_ctx *ctx, int *timed_out);
  * 0 normal, 1 evict_first, 2 evict_last; default 1100), "chunks" (1..4 independent bands per directional sweep, each a kernel chain on
  * its own stream so that kernel tails overlap; default 2 for grids of >= 2^20 cells), "peer_dbg" (development switches).
  * Fused sweeps: "fuse" (0|1, default 1: pmw_evolve launches one kernel per directional sweep), "keep_tmp"
- * (0|1, default 1: the last sweep of a pmw_evolve call also writes state_tmp), "sweep_zt" (z sweep
+ * (state_tmp after pmw_evolve: 0 never produced, 1 [default] on demand -- the call's last sweep leaves the store
+ * out and is run again with it the first time state_tmp is read or a buffer is about to change, so a loop of
+ * one-step calls that never looks at state_tmp does not pay for it; 2 written by every call), "sweep_zt" (z sweep
  * organisation: 0 streaming [default], 1 transposing), "sweep_lz" (rows per segment of the streaming z sweep;
  * 0 = chosen from the grid), "sweep_xp" (passes of 64 interfaces per x tile: 2), "dyn_items" (x sweeps draw their
  * work items from a global counter: 0 never, 1 on a slab ring [default], 2 always). */

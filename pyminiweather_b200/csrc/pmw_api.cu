@@ -116,6 +116,13 @@ struct pmw_ctx {
     cudaEvent_t ev_fork, ev_join[4];
     cudaStream_t launch_stream;  // stream the stage launch helpers use
     int cur_chunk, cur_nchunks;
+    // lazy state_tmp (keep_tmp == 1): the last sweep of a pmw_evolve call did NOT write the reference's stage-2 array;
+    // ensure_tmp re-runs that sweep with the store switched on when somebody asks for it.  Valid while the sweep's
+    // input (the spare buffer) and output (the state buffer) are what they were: every entry point that touches a
+    // buffer materialises or drops it first (BIND / BIND_KEEP).
+    bool tmp_pending;
+    int tp_dir, tp_src, tp_out;
+    double tp_dt;
     // pmw_evolve_host: copy streams (H2D, D2H) and one event per band and direction
     cudaStream_t hs_stream[2];
     std::vector<cudaEvent_t> hs_ev;
@@ -133,10 +140,27 @@ static int bind(pmw_ctx* c)
     CU_TRY(cudaSetDevice(c->p.device));
     return PMW_OK;
 }
-#define BIND(c)                   \
+static int ensure_tmp(pmw_ctx* c);
+// BIND: entry points that may read state_tmp or write any buffer -- a pending state_tmp is materialised first.
+// BIND_KEEP: entry points that leave the buffers alone or only read the state (they call ensure_tmp themselves
+// when handed PMW_BUF_TMP).
+#define BIND_KEEP(c)              \
     do {                          \
         int rc_ = bind(c);        \
         if (rc_ != PMW_OK) return rc_; \
+    } while (0)
+#define BIND(c)                                  \
+    do {                                         \
+        int rc_ = bind(c);                       \
+        if (rc_ == PMW_OK) rc_ = ensure_tmp(c);  \
+        if (rc_ != PMW_OK) return rc_;           \
+    } while (0)
+#define ENSURE_TMP_IF(c, cond)                   \
+    do {                                         \
+        if (cond) {                              \
+            int rc_ = ensure_tmp(c);             \
+            if (rc_ != PMW_OK) return rc_;       \
+        }                                        \
     } while (0)
 
 extern "C" const char* pmw_last_error(void) { return g_err; }
@@ -190,6 +214,7 @@ extern "C" int pmw_create(const pmw_params* params, pmw_ctx** out)
     c->ev_fork = nullptr;
     c->hs_stream[0] = c->hs_stream[1] = nullptr;
     c->hs_start = nullptr;
+    c->tmp_pending = false;
     c->launch_stream = nullptr;
     c->cur_chunk = 0;
     c->cur_nchunks = 1;
@@ -319,7 +344,7 @@ static int check_watchdog(pmw_ctx* c)
 
 extern "C" int pmw_synchronize(pmw_ctx* c)
 {
-    BIND(c);
+    BIND_KEEP(c);
     CU_TRY(cudaStreamSynchronize(c->stream));
     return check_watchdog(c);
 }
@@ -353,7 +378,8 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
     } else if (!strcmp(key, "fuse")) {
         c->fuse = value ? 1 : 0;
     } else if (!strcmp(key, "keep_tmp")) {
-        c->keep_tmp = value ? 1 : 0;
+        NEED(value >= 0 && value <= 2, "keep_tmp must be 0 (never), 1 (on demand) or 2 (with every call)");
+        c->keep_tmp = value;
     } else if (!strcmp(key, "sweep_lz")) {
         NEED(value == 0 || value >= 8, "sweep_lz must be 0 (automatic) or >= 8");
         c->sweep_lz = value;
@@ -379,7 +405,7 @@ extern "C" int pmw_set_tuning(pmw_ctx* c, const char* key, int value)
 
 extern "C" int pmw_get_tuning(pmw_ctx* c, const char* key, int* value)
 {
-    BIND(c);
+    BIND_KEEP(c);
     NEED(key && value, "pmw_get_tuning: null argument");
     if (!strcmp(key, "x_tr")) *value = c->x_tr;
     else if (!strcmp(key, "x_p")) *value = c->x_p;
@@ -520,7 +546,8 @@ static int check_buf(int buf)
 
 static int copy_state(pmw_ctx* c, int buf, double* host, bool to_device, bool sync)
 {
-    BIND(c);
+    BIND_KEEP(c);
+    ENSURE_TMP_IF(c, to_device || buf == PMW_BUF_TMP);
     CHECK_BUF(buf);
     NEED(host, "null host pointer");
     const size_t NX = c->p.nx + 4, rows = (size_t)NVAR * (c->p.nz + 4);
@@ -1369,6 +1396,24 @@ static int launch_sweep(pmw_ctx* c, int direction, int pS, int pO, int pT, bool 
     return PMW_OK;
 }
 
+// The reference's state_tmp after evolve is the stage-2 array of the step's last sweep (step.py:122-131).  A
+// fused sweep only stores it on request, and that store (32 B per cell) is 11 % of a time step for a caller that
+// steps once per call (the reference's driver loop, __main__.py:237) and never looks at it.  So the last sweep of a
+// pmw_evolve call leaves it out, remembers itself, and is run again with the store switched on -- from its
+// untouched input in the spare buffer, rewriting its own output with the same bits -- the first time an entry
+// point is about to read state_tmp or to change a buffer.
+static int ensure_tmp(pmw_ctx* c)
+{
+    if (!c->tmp_pending) return PMW_OK;
+    c->tmp_pending = false;
+    if (c->spare != c->tp_src || c->l2p[PMW_BUF_STATE] != c->tp_out)
+        return fail(PMW_EINVAL, "internal error: the buffers of a pending state_tmp were rotated");
+    const int T = c->l2p[PMW_BUF_TMP];
+    const int rc = launch_sweep(c, c->tp_dir, c->tp_src, c->tp_out, T, true, c->tp_dt);
+    c->xhalo_valid[T] = c->xhalo6_valid[T] = false;
+    return rc;
+}
+
 static int evolve_sweep_fused(pmw_ctx* c, int direction, double dt, bool write_tmp)
 {
     if (dt <= 0) dt = c->p.dt;
@@ -1383,12 +1428,14 @@ static int evolve_sweep_fused(pmw_ctx* c, int direction, double dt, bool write_t
 
 extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
 {
-    BIND(c);
+    BIND_KEEP(c);
     NEED(nsteps >= 0, "pmw_evolve: negative nsteps");
     NEED(c->p.periodic_x || c->peers,
          "pmw_evolve: a slab context (periodic_x=0) needs pmw_connect_peers, or must be stepped stage by "
          "stage with pmw_evolve_stage and a halo exchange before every x stage");
     if (c->jet_rows) {
+        int rc0 = ensure_tmp(c);  // (this path goes through the operator entry points, which read state_tmp)
+        if (rc0 != PMW_OK) return rc0;
         // Injection: x is not periodic, so neither the fused sweeps (6-wide periodic halo) nor the
         // stages that write the wrap for their successor apply.  Run the reference's own sequence
         // (step.py:105-143): explicit halo fill, then the fused stage kernel, per stage; arrays that
@@ -1408,6 +1455,8 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
         }
         return PMW_OK;
     }
+    if (dt <= 0) dt = c->p.dt;
+    if (nsteps > 0) c->tmp_pending = false;  // this call produces a new state_tmp (no path below reads the old one)
     // (x sweeps of a connected slab carry the halo push / epoch wait per stage: those stay whole)
     const bool chunk_ok = c->chunks > 1 && c->p.variant == PMW_VARIANT_TMA && !(c->p.nx & 1) && !c->timing;
     const bool fused = fuse_ok(c);
@@ -1420,7 +1469,16 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
 #endif
             if (fused) {
                 // state_tmp (the reference's stage-2 array) is only materialised by the last sweep of the call
-                rc = evolve_sweep_fused(c, dirs[d], dt, c->keep_tmp && n == nsteps - 1 && d == 1);
+                const bool last = n == nsteps - 1 && d == 1;
+                const bool lazy = last && c->keep_tmp == 1 && !c->peers && !c->timing;
+                rc = evolve_sweep_fused(c, dirs[d], dt, last && c->keep_tmp && !lazy);
+                if (rc == PMW_OK && lazy) {
+                    c->tmp_pending = true;
+                    c->tp_dir = dirs[d];
+                    c->tp_dt = dt;
+                    c->tp_src = c->spare;
+                    c->tp_out = c->l2p[PMW_BUF_STATE];
+                }
             } else if (chunk_ok && (!c->peers || dirs[d] == PMW_DIR_Z)) {
                 rc = evolve_sweep_chunked(c, dirs[d], dt);
             } else {
@@ -1458,10 +1516,11 @@ static int evolve_host_plain(pmw_ctx* c, double* host, double dt)
 
 extern "C" int pmw_evolve_host(pmw_ctx* c, double* host_state, double dt, int nbands)
 {
-    BIND(c);
+    BIND_KEEP(c);
     NEED(host_state, "pmw_evolve_host: null host pointer");
     NEED(nbands >= 0, "pmw_evolve_host: negative band count");
     if (dt <= 0) dt = c->p.dt;
+    c->tmp_pending = false;  // every buffer is overwritten; the tmp buffer holds the previous state afterwards
     const int nz = c->p.nz;
     const bool can_band = fuse_ok(c) && c->p.periodic_x && !c->peers && !c->jet_rows && !c->src_w && !use_zt(c) &&
                           !c->sweep_z3 && !c->timing;
@@ -1542,14 +1601,14 @@ extern "C" int pmw_evolve_host(pmw_ctx* c, double* host_state, double dt, int nb
 
 extern "C" int pmw_get_reverse_direction(pmw_ctx* c, int* reverse)
 {
-    BIND(c);
+    BIND_KEEP(c);
     NEED(reverse, "null pointer");
     *reverse = c->reverse;
     return PMW_OK;
 }
 extern "C" int pmw_set_reverse_direction(pmw_ctx* c, int reverse)
 {
-    BIND(c);
+    BIND_KEEP(c);
     c->reverse = reverse ? 1 : 0;
     return PMW_OK;
 }
@@ -1559,7 +1618,8 @@ extern "C" int pmw_set_reverse_direction(pmw_ctx* c, int reverse)
 // ---------------------------------------------------------------------------------------------
 extern "C" int pmw_stats_device(pmw_ctx* c, int buf, double* dev_out2)
 {
-    BIND(c);
+    BIND_KEEP(c);
+    ENSURE_TMP_IF(c, buf == PMW_BUF_TMP);
     CHECK_BUF(buf);
     NEED(dev_out2, "pmw_stats_device: null output");
     NEED(c->hydro_set, "pmw_stats: hydrostatic profiles not set");
@@ -1586,7 +1646,8 @@ extern "C" int pmw_stats(pmw_ctx* c, int buf, double out[2])
 
 extern "C" int pmw_solution_variables(pmw_ctx* c, int buf, double* host_out)
 {
-    BIND(c);
+    BIND_KEEP(c);
+    ENSURE_TMP_IF(c, buf == PMW_BUF_TMP);
     CHECK_BUF(buf);
     NEED(host_out, "pmw_solution_variables: null output");
     NEED(c->hydro_set, "pmw_solution_variables: hydrostatic profiles not set");
@@ -1784,7 +1845,8 @@ extern "C" int pmw_fp64_peak(pmw_ctx* c, double* warp_dfma_per_s, double* sm_clo
 // ---------------------------------------------------------------------------------------------
 extern "C" int pmw_interpolate(pmw_ctx* c, int direction, int buf, double* host_vals, double* host_d3)
 {
-    BIND(c);
+    BIND_KEEP(c);
+    ENSURE_TMP_IF(c, buf == PMW_BUF_TMP);
     CHECK_BUF(buf);
     NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_interpolate: bad direction %d", direction);
     NEED(host_vals && host_d3, "pmw_interpolate: null output");
@@ -1833,7 +1895,8 @@ extern "C" int pmw_compute_flux(pmw_ctx* c, int direction, const double* host_va
 
 extern "C" int pmw_compute_tend(pmw_ctx* c, int direction, const double* host_flux, int state_buf, double* host_tend)
 {
-    BIND(c);
+    BIND_KEEP(c);
+    ENSURE_TMP_IF(c, state_buf == PMW_BUF_TMP);
     CHECK_BUF(state_buf);
     NEED(direction == PMW_DIR_X || direction == PMW_DIR_Z, "pmw_compute_tend: bad direction %d", direction);
     NEED(host_flux && host_tend, "pmw_compute_tend: null argument");

@@ -547,3 +547,32 @@ def test_slab_halo_pack_unpack_roundtrip():
         want[:, 2:-2, :] = whole[:, 2:-2, :][:, :, cols]
         assert np.array_equal(got[:, 2:-2, :], want[:, 2:-2, :])
         slabs[r].close()
+
+
+def test_state_tmp_is_produced_on_demand_with_the_bits_of_the_eager_path():
+    """keep_tmp = 1 (default): the last sweep of pmw_evolve leaves the state_tmp store out and is re-run with it
+    when state_tmp is read or a buffer is about to change.  Same bits as keep_tmp = 2 (written by every call) and
+    as the stage-by-stage path; two launches per one-step call while nobody looks."""
+    p, case = new_case(512, 1024, "collision")   # > 0.4 M cells: streaming z sweep
+    staged, eager, lazy = solver_for(case, fuse=0), solver_for(case, keep_tmp=2), solver_for(case)
+    assert lazy.get_tuning("keep_tmp") == 1
+    for step in range(3):                       # Z,X / X,Z / Z,X: the pending sweep is an x sweep, then a z sweep
+        n0 = lazy.launch_count
+        staged.evolve(1); eager.evolve(1); lazy.evolve(1)
+        assert lazy.launch_count - n0 == 2
+        if step == 0:
+            continue                            # nobody looks after the first step: the pending sweep is dropped
+        t = lazy.download(TMP)
+        assert lazy.launch_count - n0 == 3      # the re-run
+        assert np.array_equal(interior(t), interior(eager.download(TMP)))
+        assert np.array_equal(interior(t), interior(staged.download(TMP)))
+        assert np.array_equal(interior(lazy.download(STATE)), interior(staged.download(STATE)))
+        assert lazy.launch_count - n0 == 3      # only once
+    # a buffer about to change: state_tmp of the finished step is secured first
+    staged.evolve(1); lazy.evolve(1)
+    want = staged.download(TMP)
+    lazy.upload(STATE, case.state)              # overwrites the re-run's output buffer
+    assert np.array_equal(interior(lazy.download(TMP)), interior(want))
+    assert np.array_equal(lazy.download(STATE)[:, 2:-2, 2:-2], case.state[:, 2:-2, 2:-2])
+    for s in (staged, eager, lazy):
+        s.close()
