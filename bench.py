@@ -607,6 +607,23 @@ def run_gpu(args, rank, local_rank, world):
         e2e = {"value": cells * k_e2e / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
                "d2h_bytes_per_step": nbytes * world, "steps": k_e2e, "ms_per_step": 1e3 * dt_e2e / k_e2e, "api": api,
                "bytes_note": "summed over ranks; every rank moves its own slab (host pinned memory)"}
+        if world == 1:
+            # the same call with the streamed step switched off (upload, step, download one after the other):
+            # what overlapping H2D, the sweeps and D2H band by band buys (pmw_evolve_host)
+            import pyminiweather_b200.solve.step as step_mod
+            step_mod.HOST_BANDS = 1
+            try:
+                call()
+                t0 = time.perf_counter()
+                for _ in range(max(5, k_e2e // 2)):
+                    call()
+                dt_seq = (time.perf_counter() - t0) / max(5, k_e2e // 2)
+            finally:
+                step_mod.HOST_BANDS = 0
+            e2e["sequential_ms_per_step"] = 1e3 * dt_seq
+            e2e["sequential_value"] = cells / dt_seq
+            e2e["note"] = ("evolve() on host arrays = pmw_evolve_host: the step streamed in row bands, H2D / sweeps / D2H "
+                           "overlapped (bit-identical to the sequence); sequential_* = the same call with HOST_BANDS = 1")
     solver.close()
 
     # ---- N>1: bitwise check against a single GPU; everywhere: the named shapes ----------------------

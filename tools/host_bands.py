@@ -1,5 +1,5 @@
 """The streamed host step (pmw_evolve_host) against the plain sequence upload + evolve(1) + download, on pinned host
-memory, for a list of band counts.   usage: python tools/host_bands.py nx nz [bands ...] [host_ramp=0]"""
+memory, for a list of band counts.   usage: python tools/host_bands.py nx nz [bands ...] [key=value tuning ...]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,7 +9,7 @@ from helpers import new_case, HYDRO
 from pyminiweather_b200.engine import DeviceSolver
 
 nx, nz = int(sys.argv[1]), int(sys.argv[2])
-tune = {k: int(v) for k, v in (a.split("=") for a in sys.argv[3:] if "=" in a)}   # e.g. host_ramp=0
+tune = {k: int(v) for k, v in (a.split("=") for a in sys.argv[3:] if "=" in a)}
 bands = [int(b) for b in sys.argv[3:] if "=" not in b] or [1, 2, 4, 8, 16, 32, 0]
 _, case = new_case(nx, nz, "thermal")
 pinned = torch.empty((4, nz + 4, nx + 4), dtype=torch.float64, pin_memory=True)
