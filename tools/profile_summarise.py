@@ -46,8 +46,7 @@ scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[un]
 per = [(a + b) * scale for a, b in zip(col("dram__bytes_read.sum"), col("dram__bytes_write.sum"))]
 names = [r[hh.index("Kernel Name")] for r in raw[2:]]
 json.dump({"dram_bytes_per_launch_mean": sum(per) / len(per), "per_launch": per, "kernels": names,
-           "source": f"profiles/{tag}_ncu_full_sweep_kernels.csv (ncu --set full, {len(per)} consecutive sweep launches, 2048x1024; "
-                     "the last one is the once-per-call variant that also writes state_tmp)",
+           "source": f"profiles/{tag}_ncu_full_sweep_kernels.csv (ncu --set full, {len(per)} consecutive sweep launches, 2048x1024)",
            "note": "bytes counted inside each kernel's own window; part of a kernel's output is written back from L2 after the kernel ends"},
           open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, f"{tag}_launch_list_summary.csv")).read())
