@@ -435,3 +435,25 @@ def test_strict_dropin_uses_the_streamed_step_and_matches_the_oracle():
         evolve(p, f, None, dt=p["dt"])
         no.evolve(case)
         assert worst_rel_l2(f.state, case.state) <= 1e-11
+
+
+def test_streamed_dropin_on_config_2_vs_the_reference_fixture():
+    """BASELINE config 2 (thermal 2048x1024) through the strict drop-in -- ``evolve`` on host arrays, i.e. the
+    streamed step (pmw_evolve_host, 16 bands) -- against the fixture generated from the reference's NumPy backend:
+    every 32nd cell and the per-variable norms of the whole interior after 1, 2, 5 and 10 steps (stacked metric
+    <= 1e-11; rho' at its ill-conditioned bound, see test_gpu_parity)."""
+    import os
+    from pyminiweather_b200.solve import evolve
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "evolve_thermal_2048x1024_10steps_sub32.npz"))
+    p, case = new_case(2048, 1024, "thermal")
+    f = foreign_fields(case)
+    done = 0
+    for n in (1, 2, 5, 10):
+        for _ in range(n - done):
+            evolve(p, f, None, dt=p["dt"])
+        done = n
+        got = interior(f.state)
+        sub, want = got[:, ::32, ::32], g[f"sub_{n}"]
+        assert np.linalg.norm(sub - want) / np.linalg.norm(want) <= 1e-11
+        for v in range(4):
+            assert abs(np.linalg.norm(got[v]) - g[f"l2_{n}"][v]) / g[f"l2_{n}"][v] <= (1e-9 if v == 0 else 1e-12)
