@@ -104,11 +104,18 @@ def foreign_solver(fields, params) -> DeviceSolver:
         while len(_foreign) > _MAX_FOREIGN:
             _drop(next(iter(_foreign)))
     solver = ent[1]
+    # The caller owns the profile arrays and may change them between calls: they are re-validated every time, but
+    # cheaply -- one byte string of the five profiles (and the configuration) against what this context saw last;
+    # the element-wise checks below cost 50 us per call, 3 % of a streamed 2048x1024 step
     hydro = [np.ascontiguousarray(getattr(fields, n), dtype=np.float64) for n in HYDRO_NAMES]
-    if all(np.all(h > 0) for h in hydro[:4]) and not solver.hydro_matches(hydro):
-        solver.set_hydrostatic(*hydro)
-    sync_source(solver, params, hydro[0])
-    sync_inflow(solver, params, params.get("ic_type"))
+    digest = (b"".join(h.tobytes() for h in hydro), params.get("ic_type"), params.get("xlen"), params.get("zlen"))
+    if getattr(solver, "_foreign_digest", None) != digest:
+        ok = all(np.all(h > 0) for h in hydro[:4])
+        if ok and not solver.hydro_matches(hydro):
+            solver.set_hydrostatic(*hydro)
+        sync_source(solver, params, hydro[0])
+        sync_inflow(solver, params, params.get("ic_type"))
+        solver._foreign_digest = digest if ok else None
     return solver
 
 
