@@ -1498,9 +1498,9 @@ extern "C" int pmw_evolve(pmw_ctx* c, int nsteps, double dt)
 // kernels, and upload -> step -> download one after the other uses one direction of the link at a time.
 // But a step only couples rows through the z sweep's 6-row halo (three stages x two cells), and the x sweep
 // not at all: the final rows [k0, k1) depend on the initial rows [k0-6, k1+6) alone.  So the step runs in
-// bands of rows -- band b is uploaded on one copy stream, swept (both directions, row-range launches of the
-// same fused kernels: bit-identical to the whole-grid launches) on the context's stream as soon as band b+1
-// has arrived, and downloaded on a second copy stream while later bands are still on their way up: H2D and
+// bands of rows -- band b is uploaded on one copy stream (the copies run six rows ahead of the bands), swept (both
+// directions, row-range launches of the same fused kernels: bit-identical to the whole-grid launches) on the
+// context's stream as soon as its copy has landed, and downloaded on a second copy stream while later bands are still on their way up: H2D and
 // D2H overlap and the call takes little more than ONE transfer of the state.  Buffers: the upload goes to the
 // state buffer A, the first sweep writes the spare buffer C, the second the tmp buffer B (A cannot take it:
 // later bands still read A's rows next to the band), B becomes the state.  The reference's state_tmp is
@@ -1524,8 +1524,8 @@ extern "C" int pmw_evolve_host(pmw_ctx* c, double* host_state, double dt, int nb
     const int nz = c->p.nz;
     const bool can_band = fuse_ok(c) && c->p.periodic_x && !c->peers && !c->jet_rows && !c->src_w && !use_zt(c) &&
                           !c->sweep_z3 && !c->timing;
-    if (nbands == 0)  // bands of ~64 rows (a 16 KB row at nx = 2048: ~1 MB per band and variable), 32 at most
-        nbands = std::min(32, nz / 64);
+    if (nbands == 0)  // bands of ~128 rows, 32 at most: a band-sized DMA job costs ~8 us over what its bytes cost,
+        nbands = std::min(32, nz / 128);  // the pipeline's fill and drain one band each (measured: profiles/r2bx)
     nbands = std::min(nbands, nz / 16);
     if (!can_band || nbands < 2) return evolve_host_plain(c, host_state, dt);
 
@@ -1556,20 +1556,24 @@ extern "C" int pmw_evolve_host(pmw_ctx* c, double* host_state, double dt, int nb
     auto k_lo = [&](int b) { return (int)((long long)nz * b / nbands); };          // first interior row of band b
     auto a_lo = [&](int b) { return b == 0 ? 0 : k_lo(b) + HS; };                   // ... array row (band 0: + halo rows)
     auto a_hi = [&](int b) { return b == nbands - 1 ? nz + 2 * HS : k_lo(b + 1) + HS; };
+    // uploads run six rows ahead of the bands: band b's copy ends with the six rows of band b+1 its z sweep reads (and
+    // starts after the six it shares with band b-1), so that band b can be swept as soon as its OWN copy has landed
+    auto u_lo = [&](int b) { return b == 0 ? 0 : a_lo(b) + SWEEP_HALO; };
+    auto u_hi = [&](int b) { return b == nbands - 1 ? nz + 2 * HS : a_hi(b) + SWEEP_HALO; };
 
     // earlier work of the context (kernels reading or writing the three buffers) before the first upload lands
     CU_TRY(cudaEventRecord(c->hs_start, c->stream));
     CU_TRY(cudaStreamWaitEvent(up, c->hs_start, 0));
     CU_TRY(cudaStreamWaitEvent(down, c->hs_start, 0));
     for (int b = 0; b < nbands; ++b) {
-        CU_TRY(copy_band(A, a_lo(b), a_hi(b), true, up));
+        CU_TRY(copy_band(A, u_lo(b), u_hi(b), true, up));
         CU_TRY(cudaEventRecord(c->hs_ev[b], up));
     }
     c->xhalo_valid[A] = c->xhalo6_valid[A] = false;  // every band's x sweep fills the 6-wide wrap of its rows
     int xdone = 0, rc = PMW_OK;
     for (int b = 0; b < nbands && rc == PMW_OK; ++b) {
         const int k0 = k_lo(b), k1 = k_lo(b + 1);
-        CU_TRY(cudaStreamWaitEvent(c->stream, c->hs_ev[std::min(b + 1, nbands - 1)], 0));  // rows up to k1 + 6
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->hs_ev[b], 0));  // rows up to k1 + 6 are there
         if (!xfirst) {
             rc = launch_sweep(c, PMW_DIR_Z, A, C, B, false, dt, k0, k1);
             c->xhalo_valid[C] = c->xhalo6_valid[C] = true;  // the z sweep stored the periodic images of its rows
